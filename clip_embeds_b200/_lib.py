@@ -1,0 +1,52 @@
+"""ctypes binding of libclipk.so (the C ABI declared in include/clipk.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclipk.so")
+
+c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list EVERY symbol include/clipk.h declares (tests/test_abi.py checks it).
+SIGNATURES = {
+    "clipk_last_error": (ctypes.c_char_p, []),
+    "clipk_version": (c_int, []),
+    "clipk_check_device": (c_int, []),
+    "clipk_gemm_bf16": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_i64, c_int,
+                                c_int, c_int, c_int, c_int, c_f32, c_int, c_vp]),
+}
+
+_lib = None
+
+
+class ClipkError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ClipkError(
+                f"{LIB_PATH} not found: build it with `python -m clip_embeds_b200.build` "
+                "(there is no CPU / eager fallback for this path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().clipk_last_error()
+        raise ClipkError(f"clipk error {rc}: {msg.decode() if msg else '?'}")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))

@@ -1,0 +1,119 @@
+// Error reporting, device gate and TMA tensor-map construction.
+#include <atomic>
+#include <mutex>
+
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace clipk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct DevInfo {
+  std::atomic<int> state{0};  // 0 unknown, 1 ok, 2 wrong arch
+  int sms = 0;
+};
+static DevInfo g_dev[64];
+
+static int query_device(int* dev_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("no CUDA device available (cudaGetDevice failed): the clipk kernels require a B200 (sm_100); "
+              "there is no CPU fallback");
+    return CLIPK_ERR_CUDA;
+  }
+  *dev_out = dev;
+  if (g_dev[dev].state.load(std::memory_order_acquire) == 0) {
+    int major = 0, minor = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      set_error("cudaDeviceGetAttribute failed");
+      return CLIPK_ERR_CUDA;
+    }
+    g_dev[dev].sms = sms;
+    g_dev[dev].state.store(major == 10 ? 1 : 2, std::memory_order_release);
+  }
+  return 0;
+}
+
+int check_device() {
+  int dev = 0;
+  int r = query_device(&dev);
+  if (r != 0) return r;
+  if (g_dev[dev].state.load(std::memory_order_acquire) != 1) {
+    set_error("device %d is not sm_100 (B200): the clipk kernels are sm_100a-only and have no fallback", dev);
+    return CLIPK_ERR_ARCH;
+  }
+  return 0;
+}
+
+int sm_count() {
+  int dev = 0;
+  if (query_device(&dev) != 0) return 1;
+  return g_dev[dev].sms > 0 ? g_dev[dev].sms : 1;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static std::atomic<void*> cached{nullptr};
+  void* p = cached.load(std::memory_order_acquire);
+  if (p == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      return nullptr;
+    }
+    cached.store(fn, std::memory_order_release);
+    p = fn;
+  }
+  return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                   uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows) {
+  auto encode = get_encode_fn();
+  if (encode == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return CLIPK_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_bytes & 15) != 0 ||
+      (batch > 1 && (batch_stride_bytes & 15) != 0)) {
+    set_error("TMA operand must be 16-byte aligned with 16-byte-multiple strides (base %p, row stride %llu B, "
+              "batch stride %llu B)", base, (unsigned long long)row_stride_bytes,
+              (unsigned long long)batch_stride_bytes);
+    return CLIPK_ERR_INVALID;
+  }
+  if (batch < 1) batch = 1;
+  if (batch == 1 || batch_stride_bytes == 0) batch_stride_bytes = row_stride_bytes * (rows > 0 ? rows : 1);
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride_bytes, batch_stride_bytes};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims (%llu,%llu,%llu) strides (%llu,%llu) box rows %u", (int)r,
+              (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch,
+              (unsigned long long)row_stride_bytes, (unsigned long long)batch_stride_bytes, box_rows);
+    return CLIPK_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace clipk
+
+extern "C" {
+const char* clipk_last_error(void) { return clipk::g_err; }
+int clipk_version(void) { return 100; }
+int clipk_check_device(void) { return clipk::check_device(); }
+}

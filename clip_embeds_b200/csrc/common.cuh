@@ -1,0 +1,108 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, device gate, TMA tensor maps,
+// engine launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <atomic>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/clipk.h"
+#include "gemm_engine.cuh"
+
+namespace clipk {
+
+void set_error(const char* fmt, ...);          // thread-local message returned by clipk_last_error()
+int check_device();                            // 0 if the current device is sm_100 (B200), else CLIPK_ERR_ARCH
+int sm_count();                                // SM count of the current device
+
+#define CLIPK_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      clipk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+      return CLIPK_ERR_CUDA;                                                                         \
+    }                                                                                                \
+  } while (0)
+
+#define CLIPK_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      clipk::set_error(__VA_ARGS__);        \
+      return CLIPK_ERR_INVALID;             \
+    }                                       \
+  } while (0)
+
+#define CLIPK_TRY(expr)       \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// 3-D bf16 tensor map with SWIZZLE_128B and a (64, box_rows, 1) box.
+//   dims    = (inner, rows, batch) extents in elements (exact: out-of-bounds box parts are zero-filled)
+//   strides = byte strides of dims 1 and 2 (multiples of 16)
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                   uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows);
+
+struct OperandDesc {
+  const void* ptr = nullptr;
+  bool mn_major = false;     // false: [rows][k] (k contiguous); true: [k][rows] (rows contiguous)
+  int64_t rows = 0;          // M (for A) or N (for B) extent
+  int64_t k = 0;             // reduction extent of ONE sub-batch
+  int64_t ld = 0;            // leading dimension in elements (stride of the non-contiguous matrix dim)
+  int64_t batch = 1;         // extent of the 3rd (batch) dim of the tensor
+  int64_t batch_stride = 0;  // elements
+  int bmul = 0;              // batch coordinate = b * bmul + sub * smul
+  int smul = 0;
+};
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const int* ksteps, const int* ksub,
+                int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t stream) {
+  using L = eng::SmemLayout<BN>;
+  eng::OperandMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  eng::Problem pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.M = M;
+  pb.N = N;
+  pb.batches = batches;
+  pb.tiles_m = (M + eng::BM - 1) / eng::BM;
+  pb.tiles_n = (N + BN - 1) / BN;
+  pb.num_pairs = num_pairs;
+  for (int q = 0; q < num_pairs; ++q) {
+    pb.ksteps[q] = ksteps[q];
+    pb.ksub[q] = ksub[q] > 0 ? ksub[q] : (ksteps[q] > 0 ? ksteps[q] : 1);
+    pb.a_bmul[q] = a[q].bmul; pb.a_smul[q] = a[q].smul;
+    pb.b_bmul[q] = b[q].bmul; pb.b_smul[q] = b[q].smul;
+    if (!A_MN) {
+      CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].k, a[q].rows, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, eng::BM));
+    } else {
+      CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].rows, a[q].k, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, 64));
+    }
+    if (!B_MN) {
+      CLIPK_TRY(make_tmap_bf16(&maps.b[q], b[q].ptr, b[q].k, b[q].rows, b[q].batch, b[q].ld * 2, b[q].batch_stride * 2, BN));
+    } else {
+      CLIPK_TRY(make_tmap_bf16(&maps.b[q], b[q].ptr, b[q].rows, b[q].k, b[q].batch, b[q].ld * 2, b[q].batch_stride * 2, 64));
+    }
+  }
+  const int total = pb.batches * pb.tiles_m * pb.tiles_n;
+  if (total <= 0) return 0;
+  auto kern = eng::gemm_kernel<BN, A_MN, B_MN, Epi>;
+  static std::atomic<uint64_t> attr_mask{0};   // per-device: the attribute is per context
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, eng::kThreads, L::kTotal, stream>>>(maps, pb, ep);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace clipk

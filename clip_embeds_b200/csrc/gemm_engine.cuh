@@ -1,0 +1,208 @@
+// Persistent warp-specialised tcgen05 GEMM engine for sm_100a.
+//
+//   acc[b][m, n] = sum over operand pairs q, k:  A_q[b][m, k] * B_q[b][n, k]      (bf16 x bf16 -> fp32 in TMEM)
+//
+// then a fused EPILOGUE functor consumes the fp32 accumulator straight out of TMEM (one thread = one output row,
+// 32 columns per tcgen05.ld) — nothing but what the functor writes reaches HBM.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B tiles, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=16)
+//   warp 2      : TMEM allocator (512 columns = 2 accumulator buffers of BN<=256 columns)
+//   warps 4..7  : epilogue       (tcgen05.ld 32x32b.x32; warp w owns TMEM lanes 32*(w%4)..+31)
+//
+// Operands may be K-major (k contiguous in global memory: tensor map dims (k, row, batch)) or MN-major (row index
+// contiguous: tensor map dims (row, k, batch)); both land in shared memory as 128-byte swizzled rows, see
+// ptx::umma_desc.  Tiles: BM=128 x BN x BK=64, kStages-deep ring of (A,B) stages.
+#pragma once
+#include "ptx.cuh"
+
+namespace eng {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct OperandMaps {
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+
+struct Problem {
+  int M, N;            // output extent per batch item
+  int batches;
+  int tiles_m, tiles_n;
+  int num_pairs;       // 1 or 2 operand pairs accumulated into the same tile
+  int ksteps[2];       // BK-steps per pair
+  int ksub[2];         // BK-steps per "sub-batch" (k index folds a second batch index; = ksteps when unused)
+  int a_bmul[2], a_smul[2];  // A batch coordinate = b * a_bmul + sub * a_smul
+  int b_bmul[2], b_smul[2];
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const typename Epi::Params ep) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = pb.batches * pb.tiles_m * pb.tiles_n;
+  const int tiles_per_batch = pb.tiles_m * pb.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < pb.num_pairs; ++q) {
+      ptx::prefetch_tmap(&maps.a[q]);
+      ptx::prefetch_tmap(&maps.b[q]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_base_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int rem = tile - b * tiles_per_batch;
+        const int m0 = (rem / pb.tiles_n) * BM;
+        const int n0 = (rem % pb.tiles_n) * BN;
+        for (int q = 0; q < pb.num_pairs; ++q) {
+          for (int ks = 0; ks < pb.ksteps[q]; ++ks) {
+            const int sub = ks / pb.ksub[q];
+            const int k0 = (ks - sub * pb.ksub[q]) * BK;
+            const int ab = b * pb.a_bmul[q] + sub * pb.a_smul[q];
+            const int bb = b * pb.b_bmul[q] + sub * pb.b_smul[q];
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            if constexpr (!A_MN) {
+              ptx::tma_load_3d(sa, &maps.a[q], &full_bar[stage], k0, m0, ab);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                ptx::tma_load_3d(sa + j * 8192, &maps.a[q], &full_bar[stage], m0 + j * 64, k0, ab);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_3d(sb, &maps.b[q], &full_bar[stage], k0, n0, bb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                ptx::tma_load_3d(sb + j * 8192, &maps.b[q], &full_bar[stage], n0 + j * 64, k0, bb);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[buf], bphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        uint32_t accum = 0;
+        for (int q = 0; q < pb.num_pairs; ++q) {
+          for (int ks = 0; ks < pb.ksteps[q]; ++ks) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // K-major: 16 bf16 = 32 B further along the swizzled 128 B row; MN-major: 16 k-rows = 2048 B further.
+              const uint64_t ad = A_MN ? ptx::umma_desc(sa + kk * 2048, 8192, 1024) : ptx::umma_desc(sa + kk * 32, 16, 1024);
+              const uint64_t bd = B_MN ? ptx::umma_desc(sb + kk * 2048, 8192, 1024) : ptx::umma_desc(sb + kk * 32, 16, 1024);
+              ptx::mma_bf16_ss(tmem_d, ad, bd, idesc, accum);
+              accum = 1;
+            }
+            ptx::mma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        ptx::mma_commit(&tfull_bar[buf]);         // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read
+    Epi epi(ep);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_per_batch;
+      const int rem = tile - b * tiles_per_batch;
+      const int m0 = (rem / pb.tiles_n) * BM;
+      const int n0 = (rem % pb.tiles_n) * BN;
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      ptx::mbar_wait(&tfull_bar[buf], bphase);
+      ptx::tc_fence_after();
+      const int m = m0 + q4 * 32 + lane;
+      epi.tile_begin(b, m, n0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * BN + c * 32, v);
+        ptx::tmem_ld_wait();
+        epi.chunk(b, m, n0 + c * 32, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+      epi.tile_end(b, m, n0, rem % pb.tiles_n);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace eng
