@@ -1,0 +1,432 @@
+// Cross-entropy / InfoNCE kernels.
+//
+//  (1) CE over a materialised fp32 logit / score matrix L [M, N] (all-pairs PACL scores, fp32 feature path):
+//      row LSE + per-row loss, column (max, sumexp) partials for cross-rank merging, and the gradient of
+//      w_row * CE_rows + w_col * CE_cols.   Replaces F.cross_entropy at PACL/model/pacl.py:509-512.
+//  (2) fp32 SIMT GEMM with generic strides: the fp32 feature path (reference training dtype, pacl.py:498-501 and
+//      open_clip/src/open_clip/loss.py:156-164 when features are fp32).
+//  (3) bf16 feature CE on the tcgen05 engine: logits = scale * X Y^T + bias are produced tile by tile in TMEM and
+//      reduced by the epilogue (online log-sum-exp partials) without ever being written; backward re-computes the
+//      tile, emits dL = w (softmax - onehot) as bf16 and feeds it to two engine GEMMs (dX = dL Y, dY = dL^T X).
+//      Handles ignore_index rows (labels < 0, loss.py:131-134) and label offsets (loss.py:128-130).
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "simt_util.cuh"
+
+namespace clipk {
+
+// ------------------------------------------------------------------------------------------------ (1) matrix CE
+__global__ void ce_rows_kernel(const float* __restrict__ L, int M, int N, int64_t ld, const int64_t* __restrict__ labels,
+                               int64_t label_offset, float* __restrict__ row_lse, float* __restrict__ row_loss) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* l = L + (int64_t)row * ld;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, l[n]);
+  mx = ptx::warp_max(mx);
+  float sm = 0.f;
+  for (int n = lane; n < N; n += 32) sm += expf(l[n] - mx);
+  sm = ptx::warp_sum(sm);
+  if (lane == 0) {
+    const float lse = mx + logf(sm);
+    row_lse[row] = lse;
+    if (row_loss != nullptr) {
+      const int64_t lab = labels != nullptr ? labels[row] : (int64_t)row + label_offset;
+      row_loss[row] = (lab >= 0 && lab < N) ? lse - l[lab] : 0.f;
+    }
+  }
+}
+
+// column-wise (max, sumexp) over the M local rows.  block = 32 columns x 8 row-lanes.
+__global__ void ce_cols_kernel(const float* __restrict__ L, int M, int N, int64_t ld, float* __restrict__ col_max,
+                               float* __restrict__ col_sum) {
+  __shared__ float smx[8][33], ssm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float mx = -INFINITY, sm = 0.f;
+  if (n < N) {
+    for (int m = ty; m < M; m += 8) {
+      const float v = L[(int64_t)m * ld + n];
+      if (v > mx) {
+        sm = sm * expf(mx - v) + 1.f;
+        mx = v;
+      } else {
+        sm += expf(v - mx);
+      }
+    }
+  }
+  smx[ty][tx] = mx;
+  ssm[ty][tx] = sm;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float gm = -INFINITY;
+    for (int j = 0; j < 8; ++j) gm = fmaxf(gm, smx[j][tx]);
+    float gs = 0.f;
+    for (int j = 0; j < 8; ++j)
+      if (smx[j][tx] > -INFINITY) gs += ssm[j][tx] * expf(smx[j][tx] - gm);
+    col_max[n] = gm;
+    col_sum[n] = gs;
+  }
+}
+
+// dL[i,k] = w_row (exp(L - rlse_i) - [k == lab_i]) + w_col (exp(L - clse_k) - [k == lab_i]),  lab_i = i + offset
+__global__ void ce_scores_grad_kernel(const float* __restrict__ L, int M, int N, int64_t ld,
+                                      const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                                      int64_t label_offset, float w_row, float w_col, float* __restrict__ dL) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int i = (int)(idx / N), k = (int)(idx % N);
+  const float v = L[(int64_t)i * ld + k];
+  const float hit = ((int64_t)k == (int64_t)i + label_offset) ? 1.f : 0.f;
+  float g = 0.f;
+  if (w_row != 0.f) g += w_row * (expf(v - row_lse[i]) - hit);
+  if (w_col != 0.f) g += w_col * (expf(v - col_lse[k]) - hit);
+  dL[idx] = g;
+}
+
+// dL[i,k] = w[i] (exp(L - rlse_i) - [k == lab_i]) with explicit labels (ignore rows: w[i] = 0)
+__global__ void ce_rows_grad_kernel(const float* __restrict__ L, int M, int N, int64_t ld,
+                                    const float* __restrict__ row_lse, const int64_t* __restrict__ labels,
+                                    int64_t label_offset, const float* __restrict__ w, float* __restrict__ dL) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int i = (int)(idx / N), k = (int)(idx % N);
+  const int64_t lab = labels != nullptr ? labels[i] : (int64_t)i + label_offset;
+  const float wi = w[i];
+  dL[idx] = wi == 0.f ? 0.f : wi * (expf(L[(int64_t)i * ld + k] - row_lse[i]) - ((int64_t)k == lab ? 1.f : 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------ (2) fp32 GEMM
+// C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + beta * C[m*ldc + n]; 64x64 tile, 4x4 per thread.
+__global__ void __launch_bounds__(256)
+sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbk,
+                     int64_t sbn, float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int r, kk;
+      if (sak == 1) { kk = e & 15; r = e >> 4; } else { r = e & 63; kk = e >> 6; }
+      const int m = m0 + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f;
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int c, kk;
+      if (sbk == 1) { kk = e & 15; c = e >> 4; } else { c = e & 63; kk = e >> 6; }
+      const int n = n0 + c, k = k0 + kk;
+      Bs[kk][c] = (n < N && k < K) ? B[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float* c = C + (int64_t)m * ldc + n;
+      *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+    }
+  }
+}
+
+}  // namespace clipk
+
+// ------------------------------------------------------------------------------------------------ (3) engine CE
+namespace epi {
+
+// per-(row, n-tile) online log-sum-exp partial of logits = scale * acc + bias; captures the label logit.
+struct LsePart {
+  struct Params {
+    float2* part;            // [M][tiles_n] (max, sumexp)
+    float* pos;              // [M] logit at the label column (written by the tile that owns it)
+    const int64_t* labels;   // nullable
+    int64_t label_offset;
+    int M, N, tiles_n;
+    float scale, bias;
+  };
+  Params p;
+  float mx, sm;
+  int64_t lab;
+  __device__ explicit LsePart(const Params& pp) : p(pp), mx(0.f), sm(0.f), lab(-1) {}
+  __device__ void tile_begin(int, int m, int) {
+    mx = -INFINITY;
+    sm = 0.f;
+    lab = -1;
+    if (m < p.M) lab = p.labels != nullptr ? p.labels[m] : (int64_t)m + p.label_offset;
+  }
+  __device__ void chunk(int, int m, int n, float* v) {
+    if (m >= p.M || n >= p.N) return;
+    float cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = fmaf(v[j], p.scale, p.bias);
+      if (n + j < p.N) cm = fmaxf(cm, v[j]);
+    }
+    const float nm = fmaxf(mx, cm);
+    float acc = sm * __expf(mx - nm);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) acc += __expf(v[j] - nm);
+    sm = acc;
+    mx = nm;
+    if (lab >= n && lab < (int64_t)n + 32 && lab < p.N) {
+      float pv = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if ((int64_t)(n + j) == lab) pv = v[j];
+      p.pos[m] = pv;
+    }
+  }
+  __device__ void tile_end(int, int m, int, int tn) {
+    if (m < p.M) p.part[(int64_t)m * p.tiles_n + tn] = make_float2(mx, sm);
+  }
+};
+
+// dL[m][n] = w[m] (exp(logit - lse[m]) - [n == label_m])  as bf16, leading dim ldd
+struct DlOut {
+  struct Params {
+    const float* lse;        // [M]
+    const float* w;          // [M]
+    const int64_t* labels;   // nullable
+    int64_t label_offset;
+    __nv_bfloat16* dL;       // [M][ldd]
+    int64_t ldd;
+    int M, N;
+    float scale, bias;
+  };
+  Params p;
+  float lse, w;
+  int64_t lab;
+  __device__ explicit DlOut(const Params& pp) : p(pp), lse(0.f), w(0.f), lab(-1) {}
+  __device__ void tile_begin(int, int m, int) {
+    if (m < p.M) {
+      lse = p.lse[m];
+      w = p.w[m];
+      lab = p.labels != nullptr ? p.labels[m] : (int64_t)m + p.label_offset;
+    }
+  }
+  __device__ void chunk(int, int m, int n, float* v) {
+    if (m >= p.M || n >= p.N) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float l = fmaf(v[j], p.scale, p.bias);
+      const float hit = ((int64_t)(n + j) == lab) ? 1.f : 0.f;
+      v[j] = (w == 0.f) ? 0.f : w * (__expf(l - lse) - hit);
+    }
+    store_bf16x32(p.dL + (int64_t)m * p.ldd + n, v, min(32, p.N - n));
+  }
+  __device__ void tile_end(int, int, int, int) {}
+};
+
+}  // namespace epi
+
+namespace clipk {
+
+__global__ void lse_merge_kernel(const float2* __restrict__ part, const float* __restrict__ pos, int M, int tiles_n,
+                                 const int64_t* __restrict__ labels, int64_t label_offset, int N,
+                                 float* __restrict__ row_lse, float* __restrict__ row_loss) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float mx = -INFINITY;
+  for (int t = 0; t < tiles_n; ++t) mx = fmaxf(mx, part[(int64_t)m * tiles_n + t].x);
+  float sm = 0.f;
+  for (int t = 0; t < tiles_n; ++t) {
+    const float2 q = part[(int64_t)m * tiles_n + t];
+    if (q.x > -INFINITY) sm += q.y * expf(q.x - mx);
+  }
+  const float lse = mx + logf(sm);
+  row_lse[m] = lse;
+  const int64_t lab = labels != nullptr ? labels[m] : (int64_t)m + label_offset;
+  row_loss[m] = (lab >= 0 && lab < N) ? lse - pos[m] : 0.f;
+}
+
+static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kCeChunkRows = 4096;
+
+struct CeWorkspace {
+  float2* part;
+  float* pos;
+  __nv_bfloat16* dL;
+};
+static size_t ce_carve(CeWorkspace* w, void* base, int M, int N) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  };
+  const int tiles_n = (N + 255) / 256;
+  const int mc = M < kCeChunkRows ? M : kCeChunkRows;
+  w->part = static_cast<float2*>(take((size_t)M * tiles_n * sizeof(float2)));
+  w->pos = static_cast<float*>(take((size_t)M * 4));
+  w->dL = static_cast<__nv_bfloat16*>(take((size_t)mc * round_up_i(N, 64) * 2));
+  return off;
+}
+
+int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
+                const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+  CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_fwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
+  CeWorkspace w{};
+  const size_t need = ce_carve(&w, ws, M, N);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "ce_feat_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  OperandDesc a, b;
+  a.ptr = X; a.rows = M; a.k = D; a.ld = D;
+  b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
+  const int ks[1] = {(D + 63) / 64};
+  const int tiles_n = (N + 255) / 256;
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
+  epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
+  CLIPK_TRY(launch_gemm<256, false, false, epi::LsePart>(&a, &b, 1, ks, ks, M, N, 1, ep, st));
+  lse_merge_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
+                const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
+                int accX, float* dY, int accY, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_bwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
+  CeWorkspace w{};
+  const size_t need = ce_carve(&w, ws, M, N);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "ce_feat_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int64_t ldd = round_up_i(N, 64);
+  const int ksD[1] = {(D + 63) / 64};
+  for (int m0 = 0; m0 < M; m0 += kCeChunkRows) {
+    const int mc = (M - m0) < kCeChunkRows ? (M - m0) : kCeChunkRows;
+    // recompute logits tile -> dL (bf16)
+    {
+      OperandDesc a, b;
+      a.ptr = X + (int64_t)m0 * D; a.rows = mc; a.k = D; a.ld = D;
+      b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
+      epi::DlOut::Params ep{row_lse + m0, row_w + m0, labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0),
+                            w.dL, ldd, mc, N, scale, bias};
+      CLIPK_TRY(launch_gemm<256, false, false, epi::DlOut>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st));
+    }
+    // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
+    if (dX != nullptr) {
+      OperandDesc a, b;
+      a.ptr = w.dL; a.rows = mc; a.k = N; a.ld = ldd;
+      b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
+      const int ks[1] = {(N + 63) / 64};
+      epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX};
+      CLIPK_TRY(launch_gemm<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, 1, ep, st));
+    }
+    // dY (+)= scale * dL^T X[m0:m0+mc]        (A = dL MN-major (rows = n), B = X MN-major)
+    if (dY != nullptr) {
+      OperandDesc a, b;
+      a.ptr = w.dL; a.mn_major = true; a.rows = N; a.k = mc; a.ld = ldd;
+      b.ptr = X + (int64_t)m0 * D; b.mn_major = true; b.rows = D; b.k = mc; b.ld = D;
+      const int ks[1] = {(mc + 63) / 64};
+      epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0};
+      CLIPK_TRY(launch_gemm<256, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, N, D, 1, ep, st));
+    }
+  }
+  return 0;
+}
+
+}  // namespace clipk
+
+extern "C" {
+
+int clipk_ce_rows(const float* L, int M, int N, int64_t ld, const int64_t* labels, int64_t label_offset,
+                  float* row_lse, float* row_loss, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_rows: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
+  if (M == 0) return 0;
+  clipk::ce_rows_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, labels, label_offset,
+                                                                                    row_lse, row_loss);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, float* col_sum, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_cols: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
+  clipk::ce_cols_kernel<<<(N + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, col_max, col_sum);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_ce_scores_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const float* col_lse,
+                         int64_t label_offset, float w_row, float w_col, float* dL, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_scores_grad: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
+  if (M == 0) return 0;
+  const int64_t n = (int64_t)M * N;
+  clipk::ce_scores_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      L, M, N, ld, row_lse, col_lse, label_offset, w_row, w_col, dL);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_ce_rows_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const int64_t* labels,
+                       int64_t label_offset, const float* row_w, float* dL, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_rows_grad: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
+  if (M == 0) return 0;
+  const int64_t n = (int64_t)M * N;
+  clipk::ce_rows_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      L, M, N, ld, row_lse, labels, label_offset, row_w, dL);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                    int64_t ldc, int M, int N, int K, float alpha, float beta, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: bad shape");
+  if (M == 0 || N == 0) return 0;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  clipk::sgemm_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc, M,
+                                                                                   N, K, alpha, beta);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t clipk_ce_feat_workspace_bytes(int M, int N) {
+  clipk::CeWorkspace w{};
+  return clipk::ce_carve(&w, nullptr, M, N);
+}
+
+int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                      const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
+                      size_t ws_bytes, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::ce_feat_fwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
+                            bias, labels, label_offset, row_lse, row_loss, workspace, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                      const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
+                      int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
+                            bias, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, workspace, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+}

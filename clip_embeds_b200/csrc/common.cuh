@@ -35,10 +35,10 @@ int sm_count();                                // SM count of the current device
     }                                       \
   } while (0)
 
-#define CLIPK_TRY(expr)       \
-  do {                        \
-    int _r = (expr);          \
-    if (_r != 0) return _r;   \
+#define CLIPK_TRY(...)          \
+  do {                          \
+    int _r = (__VA_ARGS__);     \
+    if (_r != 0) return _r;     \
   } while (0)
 
 // 3-D bf16 tensor map with SWIZZLE_128B and a (64, box_rows, 1) box.

@@ -1,6 +1,7 @@
 // Fused epilogue functors for eng::gemm_kernel.  One thread owns one output row `m`; chunk() receives 32
 // consecutive fp32 accumulator columns [n, n+32) of that row.
 #pragma once
+#include "../../include/clipk.h"
 #include "ptx.cuh"
 
 namespace epi {
@@ -89,6 +90,249 @@ struct Store {
         store_f32x32(dst, v, valid);
       }
     }
+  }
+  __device__ void tile_end(int, int, int, int) {}
+};
+
+}  // namespace epi
+
+namespace epi {
+
+__device__ __forceinline__ void store_f16x32(__half* dst, const float* v, int valid) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 p0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
+      __half2 p1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+      __half2 p2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+      __half2 p3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2);
+      u.w = *reinterpret_cast<uint32_t*>(&p3);
+      d4[j] = u;
+    }
+  } else {
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dst[j] = __float2half(v[j]);
+  }
+}
+__device__ __forceinline__ void load_f16x32(const __half* src, float* v, int valid) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u = s4[j];
+      const __half2* p = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(p[t]);
+        v[8 * j + 2 * t] = f.x;
+        v[8 * j + 2 * t + 1] = f.y;
+      }
+    }
+  } else {
+    for (int j = 0; j < 32; ++j) v[j] = (j < valid) ? __half2float(src[j]) : 0.f;
+  }
+}
+
+__device__ __forceinline__ float fast_sigmoid10(float s) { return __frcp_rn(1.f + __expf(-10.f * s)); }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1
+// acc[m=text k][n=patch p] = <T_k, V_ip> (raw).  s = acc * rnT[k] * rnV[i,p];  a = sigmoid(10 s)  (pacl.py:133)
+// writes A (bf16, zero in the pad columns), optionally S (fp16), and num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
+struct PaclAct {
+  struct Params {
+    const float* rnV;   // [batch][P]
+    const float* rnT;   // [M]
+    __nv_bfloat16* A;   // [batch][M][Ppad]
+    __half* S;          // [batch][M][Ppad] or nullptr
+    float* num;         // [batch][M] or nullptr
+    int M, P, Ppad, act;
+  };
+  Params p;
+  float rt, acc;
+  __device__ explicit PaclAct(const Params& pp) : p(pp), rt(0.f), acc(0.f) {}
+  __device__ void tile_begin(int, int m, int) {
+    acc = 0.f;
+    rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
+  }
+  __device__ void chunk(int b, int m, int n, float* v) {
+    if (m >= p.M || n >= p.Ppad) return;
+    const float* rn = p.rnV + (int64_t)b * p.P;
+    float s[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int pp = n + j;
+      if (pp < p.P) {
+        const float r = v[j] * rt;
+        const float sj = r * __ldg(rn + pp);
+        const float a = (p.act == CLIPK_ACT_ONES) ? 1.f : bf16_round(fast_sigmoid10(sj));
+        acc = fmaf(a, r, acc);
+        v[j] = a;
+        s[j] = sj;
+      } else {
+        v[j] = 0.f;
+        s[j] = 0.f;
+      }
+    }
+    const int valid = min(32, p.Ppad - n);
+    const int64_t off = ((int64_t)b * p.M + m) * p.Ppad + n;
+    store_bf16x32(p.A + off, v, valid);
+    if (p.S != nullptr) store_f16x32(p.S + off, s, valid);
+  }
+  __device__ void tile_end(int b, int m, int, int) {
+    if (p.num != nullptr && m < p.M) atomicAdd(p.num + (int64_t)b * p.M + m, acc);
+  }
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (fwd)
+// acc = u_ik[d];  usq[i,k] += sum_d u^2   (the pooled vector itself never leaves the SM)
+struct Usq {
+  struct Params {
+    float* usq;   // [batch][M]
+    int M, N;
+  };
+  Params p;
+  float acc;
+  __device__ explicit Usq(const Params& pp) : p(pp), acc(0.f) {}
+  __device__ void tile_begin(int, int, int) { acc = 0.f; }
+  __device__ void chunk(int, int m, int n, float* v) {
+    if (m >= p.M || n >= p.N) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) acc = fmaf(v[j], v[j], acc);
+  }
+  __device__ void tile_end(int b, int m, int, int) {
+    if (m < p.M) atomicAdd(p.usq + (int64_t)b * p.M + m, acc);
+  }
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (bwd)
+// acc = u_ik[d];  G_ik = alpha_ik t^_k - beta_ik u_ik   (grad wrt the un-normalised pooled vector), stored bf16
+struct GOut {
+  struct Params {
+    const float* alpha;        // [batch][M]
+    const float* beta;         // [batch][M]
+    const __nv_bfloat16* T;    // [M][N]
+    const float* rnT;          // [M]
+    __nv_bfloat16* G;          // [batch][M][N]
+    int M, N;
+  };
+  Params p;
+  float al, be;
+  __device__ explicit GOut(const Params& pp) : p(pp), al(0.f), be(0.f) {}
+  __device__ void tile_begin(int b, int m, int) {
+    if (m < p.M) {
+      al = __ldg(p.alpha + (int64_t)b * p.M + m) * __ldg(p.rnT + m);
+      be = __ldg(p.beta + (int64_t)b * p.M + m);
+    }
+  }
+  __device__ void chunk(int b, int m, int n, float* v) {
+    if (m >= p.M || n >= p.N) return;
+    const int valid = min(32, p.N - n);
+    float t[32];
+    load_bf16x32(p.T + (int64_t)m * p.N + n, t, valid);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = al * t[j] - be * v[j];
+    store_bf16x32(p.G + ((int64_t)b * p.M + m) * p.N + n, v, valid);
+  }
+  __device__ void tile_end(int, int, int, int) {}
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM3 (bwd)
+// acc = da_ikp = <G_ik, V_ip>.  ds = da * 10 a (1 - a);
+//   DS'[i,k,p] = ds * rnV[i,p] * rnT[k]      (operand of dV += DS'^T T)
+//   E  [i,k,p] = ds * rnV[i,p] + alpha_ik a  (operand of dt^ += E V; the alpha term is the direct d score / d t^)
+//   dsdot[i,p] += sum_k ds * s               (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
+struct DsOut {
+  struct Params {
+    const __nv_bfloat16* A;  // [batch][M][Ppad]
+    const __half* S;         // [batch][M][Ppad]
+    const float* rnV;        // [batch][P]
+    const float* rnT;        // [M]
+    const float* alpha;      // [batch][M]
+    __nv_bfloat16* DS;       // [batch][M][Ppad]
+    __nv_bfloat16* E;        // [batch][M][Ppad]
+    float* dsdot;            // [batch][P]
+    int M, P, Ppad, act;
+  };
+  Params p;
+  float rt, al;
+  __device__ explicit DsOut(const Params& pp) : p(pp), rt(0.f), al(0.f) {}
+  __device__ void tile_begin(int b, int m, int) {
+    rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
+    al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f;
+  }
+  __device__ void chunk(int b, int m, int n, float* v) {
+    if (n >= p.Ppad) return;     // warp-uniform
+    const bool row_ok = m < p.M;
+    const int valid = min(32, p.Ppad - n);
+    const int64_t off = ((int64_t)b * p.M + (row_ok ? m : 0)) * p.Ppad + n;
+    float a[32], s[32];
+    if (row_ok) {
+      load_bf16x32(p.A + off, a, valid);
+      load_f16x32(p.S + off, s, valid);
+    }
+    const float* rn = p.rnV + (int64_t)b * p.P;
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int pp = n + j;
+      if (row_ok && pp < p.P) {
+        const float ds = (p.act == CLIPK_ACT_ONES) ? 0.f : v[j] * 10.f * a[j] * (1.f - a[j]);
+        const float dsv = ds * __ldg(rn + pp);
+        e[j] = fmaf(al, a[j], dsv);
+        v[j] = dsv * rt;
+        s[j] = ds * s[j];
+      } else {
+        e[j] = 0.f;
+        v[j] = 0.f;
+        s[j] = 0.f;
+      }
+    }
+    if (row_ok) {
+      store_bf16x32(p.DS + off, v, valid);
+      store_bf16x32(p.E + off, e, valid);
+    }
+    const float cs = ptx::warp_colsum32(s);   // lane j: sum over this warp's 32 rows of column n + j
+    const int col = n + (int)ptx::lane_id();
+    if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
+  }
+  __device__ void tile_end(int, int, int, int) {}
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, dV (bwd)
+// acc[m=patch p][n=d] = sum_k a_ikp G_ik[d] + sum_k DS'_ikp T_k[d];  dV_ip = acc - rnV_ip^2 dsdot_ip V_ip
+struct DvOut {
+  struct Params {
+    const __nv_bfloat16* V;   // [batch][M][N]
+    const float* rnV;         // [batch][M]
+    const float* dsdot;       // [batch][M]
+    __nv_bfloat16* dV;        // [batch][M][N]
+    int M, N;
+  };
+  Params p;
+  float coef;
+  __device__ explicit DvOut(const Params& pp) : p(pp), coef(0.f) {}
+  __device__ void tile_begin(int b, int m, int) {
+    if (m < p.M) {
+      const float r = __ldg(p.rnV + (int64_t)b * p.M + m);
+      coef = r * r * __ldg(p.dsdot + (int64_t)b * p.M + m);
+    }
+  }
+  __device__ void chunk(int b, int m, int n, float* v) {
+    if (m >= p.M || n >= p.N) return;
+    const int valid = min(32, p.N - n);
+    const int64_t off = ((int64_t)b * p.M + m) * p.N + n;
+    float x[32];
+    load_bf16x32(p.V + off, x, valid);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(-coef, x[j], v[j]);
+    store_bf16x32(p.dV + off, v, valid);
   }
   __device__ void tile_end(int, int, int, int) {}
 };

@@ -1,0 +1,299 @@
+// PACL all-pairs text-conditioned scoring, forward and backward (BASELINE north_star (1)-(3)).
+//
+//   score[i,k] = c * < n(u_ik), n(t_k) >,   u_ik = sum_p sigmoid(10 <n(t_k), n(V_ip)>) V_ip
+//
+// Reference semantics: the eval call `model(img_i, texts)` of PACL/eval_pacl.py:53-57 / :303-309 (one image, all
+// texts, diagonal of `c * image_features @ text_features.T`) looped over images; patch_alignment = pacl.py:120-133,
+// pooling + normalise = pacl.py:143-145.
+//
+// Images are processed in GROUPS of `group` images.  Within a group every contraction is one launch of the
+// tcgen05 engine with a fused epilogue; the [group, Bt, P] activation tiles live in a caller-provided scratch that
+// is re-used by every group (sized to stay L2-resident), so the [Bi, Bt, P] tensor is never materialised in HBM and
+// only O(Bi*Bt) + O(Bi*P) statistics are saved for backward (recompute, flash-style).
+//
+//  forward :  K1  A = act(T V_i^T)            (epilogue PaclAct: also num = <u, t^>)
+//             K2  u = A V_i  -> usq = |u|^2   (epilogue Usq: u never stored)
+//  backward:  K1  (recompute A, + S)          K2' G = alpha t^ - beta u          (epilogue GOut)
+//             K4  da = G V_i^T -> DS', E, dsdot (epilogue DsOut)
+//             K5  dt^ += E V                  (K folds (image, patch); fp32 accumulate)
+//             K6  dV_i = A^T G + DS'^T T - rnV^2 dsdot V   (two operand pairs, epilogue DvOut)
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "simt_util.cuh"
+
+namespace clipk {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// rn[row] = 1 / max(||x_row||, 1e-12)      (F.normalize denominator, pacl.py:122,125)
+__global__ void rownorm_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t rows, int D, float* __restrict__ rn) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* x = X + row * D;
+  float acc = 0.f;
+  for (int d = lane * 8; d < D; d += 256) {
+    float v[8];
+    simt::load8<__nv_bfloat16>(x + d, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+  }
+  acc = ptx::warp_sum(acc);
+  if (lane == 0) rn[row] = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+}
+
+__global__ void allpairs_scores_kernel(const float* __restrict__ num, const float* __restrict__ usq, int64_t n, float c,
+                                       float* __restrict__ scores) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scores[i] = c * num[i] / fmaxf(sqrtf(usq[i]), 1e-12f);
+}
+
+// alpha = g / |u|, beta = g <u,t^> / |u|^3 with g = c * dscore   (Jacobian of n(u) contracted with t^)
+__global__ void allpairs_alpha_beta_kernel(const float* __restrict__ num, const float* __restrict__ usq,
+                                           const float* __restrict__ dscore, int64_t n, float c,
+                                           float* __restrict__ alpha, float* __restrict__ beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float un = sqrtf(usq[i]);
+  const float g = c * dscore[i];
+  if (un < 1e-12f) {   // clamped normalisation: u / eps is linear, no projection term
+    alpha[i] = g * 1e12f;
+    beta[i] = 0.f;
+  } else {
+    const float r = 1.f / un;
+    alpha[i] = g * r;
+    beta[i] = g * num[i] * r * r * r;
+  }
+}
+
+// dT_k = rnT_k (dth_k - t^_k <t^_k, dth_k>),  t^ = T rnT      (Jacobian of F.normalize on the text side)
+__global__ void dtext_finalize_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT,
+                                      const float* __restrict__ dth, int Bt, int D, float* __restrict__ dT) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Bt) return;
+  const int lane = threadIdx.x & 31;
+  const float rt = rnT[row];
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, dth[(int64_t)row * D + d], dot);
+  dot = ptx::warp_sum(dot);
+  for (int d = lane; d < D; d += 32) {
+    const float th = __bfloat162float(T[(int64_t)row * D + d]) * rt;
+    dT[(int64_t)row * D + d] = rt * (dth[(int64_t)row * D + d] - th * dot);
+  }
+}
+
+struct ApWorkspace {
+  __nv_bfloat16 *A, *G, *DS, *E;
+  __half* S;
+  float *dsdot, *alpha, *beta, *dth;
+};
+
+static size_t ap_carve(ApWorkspace* w, void* base, int Bi, int Bt, int P, int D, int group, int backward) {
+  const int Ppad = round_up(P, 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  };
+  const size_t act = (size_t)group * Bt * Ppad * 2;
+  w->A = static_cast<__nv_bfloat16*>(take(act));
+  if (backward) {
+    w->S = static_cast<__half*>(take(act));
+    w->DS = static_cast<__nv_bfloat16*>(take(act));
+    w->E = static_cast<__nv_bfloat16*>(take(act));
+    w->G = static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
+    w->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
+    w->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    w->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    w->dth = static_cast<float*>(take((size_t)Bt * D * 4));
+  }
+  return off;
+}
+
+static int pick_bn(int n) {
+  // largest tile whose padding waste stays under ~12%, else the waste-free 64-multiple
+  const int cands[3] = {256, 192, 128};
+  for (int c : cands) {
+    const int cover = round_up(n, c);
+    if ((cover - n) * 8 <= n) return c;
+  }
+  return 64;
+}
+
+// K1: A = act(T V^T) for `gi` images starting at V0.
+static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, int Bt, int P, int D, int act,
+                     const float* rnV0, const float* rnT, const ApWorkspace& w, bool with_s, float* num0,
+                     cudaStream_t st) {
+  const int Ppad = round_up(P, 64);
+  OperandDesc a, b;
+  a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
+  b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
+  const int ks[1] = {(D + 63) / 64};
+  epi::PaclAct::Params ep{rnV0, rnT, w.A, with_s ? w.S : nullptr, num0, Bt, P, Ppad, act};
+  switch (pick_bn(Ppad)) {
+    case 256: return launch_gemm<256, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 192: return launch_gemm<192, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 128: return launch_gemm<128, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    default: return launch_gemm<64, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+  }
+}
+
+// K2 operands: A = activations [gi][Bt][Ppad] (K-major), B = V [gi][P][D] viewed MN-major (N = d, K = p)
+static void k2_operands(const ApWorkspace& w, const __nv_bfloat16* V0, int gi, int Bt, int P, int D, OperandDesc* a,
+                        OperandDesc* b) {
+  const int Ppad = round_up(P, 64);
+  a->ptr = w.A; a->rows = Bt; a->k = Ppad; a->ld = Ppad; a->batch = gi; a->batch_stride = (int64_t)Bt * Ppad; a->bmul = 1;
+  b->ptr = V0; b->mn_major = true; b->rows = D; b->k = P; b->ld = D; b->batch = gi; b->batch_stride = (int64_t)P * D; b->bmul = 1;
+}
+
+template <class Epi, bool A_MN>
+static int launch_nd(const OperandDesc* a, const OperandDesc* b, int npairs, const int* ks, const int* ksub, int M,
+                     int D, int batches, const typename Epi::Params& ep, cudaStream_t st) {
+  // N = D output columns, B operand MN-major (d contiguous)
+  switch (pick_bn(D)) {
+    case 256: return launch_gemm<256, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    case 192: return launch_gemm<192, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    case 128: return launch_gemm<128, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    default: return launch_gemm<64, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
+  }
+}
+
+static int validate(int Bi, int Bt, int P, int D, int act, int group) {
+  CLIPK_REQUIRE(Bi > 0 && Bt > 0 && P > 0 && D > 0, "pacl_allpairs: empty problem (Bi=%d Bt=%d P=%d D=%d)", Bi, Bt, P, D);
+  CLIPK_REQUIRE(D % 8 == 0, "pacl_allpairs: D=%d must be a multiple of 8 (16-byte rows for TMA)", D);
+  CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES, "pacl_allpairs: bad activation %d", act);
+  CLIPK_REQUIRE(group >= 1, "pacl_allpairs: group must be >= 1");
+  return 0;
+}
+
+int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
+                 float* rnV, float* rnT, float* num, float* usq, float* scores, void* ws, size_t ws_bytes, int group,
+                 cudaStream_t st) {
+  CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
+  ApWorkspace w{};
+  const size_t need = ap_carve(&w, ws, Bi, Bt, P, D, group, 0);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int Ppad = round_up(P, 64);
+  rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
+  rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
+  for (int i0 = 0; i0 < Bi; i0 += group) {
+    const int gi = (Bi - i0) < group ? (Bi - i0) : group;
+    const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w, false, num + (int64_t)i0 * Bt, st));
+    OperandDesc a, b;
+    k2_operands(w, V0, gi, Bt, P, D, &a, &b);
+    const int ks[1] = {Ppad / 64};
+    epi::Usq::Params ep{usq + (int64_t)i0 * Bt, Bt, D};
+    CLIPK_TRY(launch_nd<epi::Usq, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, st));
+  }
+  const int64_t n = (int64_t)Bi * Bt;
+  allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
+                 const float* rnV, const float* rnT, const float* num, const float* usq, const float* dscores,
+                 __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, cudaStream_t st) {
+  CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
+  ApWorkspace w{};
+  const size_t need = ap_carve(&w, ws, Bi, Bt, P, D, group, 1);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int Ppad = round_up(P, 64);
+  const int64_t n = (int64_t)Bi * Bt;
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dsdot, 0, (size_t)Bi * P * 4, st));
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)Bt * D * 4, st));
+  allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, w.alpha, w.beta);
+  for (int i0 = 0; i0 < Bi; i0 += group) {
+    const int gi = (Bi - i0) < group ? (Bi - i0) : group;
+    const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
+    const float* rnV0 = rnV + (int64_t)i0 * P;
+    const float* alpha0 = w.alpha + (int64_t)i0 * Bt;
+    const float* beta0 = w.beta + (int64_t)i0 * Bt;
+    float* dsdot0 = w.dsdot + (int64_t)i0 * P;
+    // K1 (recompute activations + scores)
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, true, nullptr, st));
+    // K2': G = alpha t^ - beta u
+    {
+      OperandDesc a, b;
+      k2_operands(w, V0, gi, Bt, P, D, &a, &b);
+      const int ks[1] = {Ppad / 64};
+      epi::GOut::Params ep{alpha0, beta0, T, rnT, w.G, Bt, D};
+      CLIPK_TRY(launch_nd<epi::GOut, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, st));
+    }
+    // K4: da = G V^T -> DS', E, dsdot
+    {
+      OperandDesc a, b;
+      a.ptr = w.G; a.rows = Bt; a.k = D; a.ld = D; a.batch = gi; a.batch_stride = (int64_t)Bt * D; a.bmul = 1;
+      b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
+      const int ks[1] = {(D + 63) / 64};
+      epi::DsOut::Params ep{w.A, w.S, rnV0, rnT, alpha0, w.DS, w.E, dsdot0, Bt, P, Ppad, act};
+      int r;
+      switch (pick_bn(Ppad)) {
+        case 256: r = launch_gemm<256, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
+        case 192: r = launch_gemm<192, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
+        case 128: r = launch_gemm<128, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
+        default: r = launch_gemm<64, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
+      }
+      CLIPK_TRY(r);
+    }
+    // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch)
+    {
+      OperandDesc a, b;
+      a.ptr = w.E; a.rows = Bt; a.k = Ppad; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
+      b.ptr = V0; b.mn_major = true; b.rows = D; b.k = P; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 0; b.smul = 1;
+      const int ks[1] = {gi * (Ppad / 64)};
+      const int ksub[1] = {Ppad / 64};
+      epi::Store<false>::Params ep{w.dth, D, 0, Bt, D, 1.f, 1};
+      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, 1, ep, st));
+    }
+    // K6: dV_i = A_i^T G_i + DS'_i^T T - rnV^2 dsdot V
+    {
+      OperandDesc a[2], b[2];
+      a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = Ppad; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
+      a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
+      b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
+      b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
+      a[1] = a[0]; a[1].ptr = w.DS;
+      b[1].ptr = T; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
+      const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
+      epi::DvOut::Params ep{V0, rnV0, dsdot0, dV + (int64_t)i0 * P * D, P, D};
+      CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, st));
+    }
+  }
+  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, Bt, D, dT);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace clipk
+
+extern "C" {
+
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int backward) {
+  clipk::ApWorkspace w{};
+  return clipk::ap_carve(&w, nullptr, Bi, Bt, P, D, group, backward);
+}
+
+int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
+                            float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
+                            int group, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::allpairs_fwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
+                             act, c, rnV, rnT, num, usq, scores, workspace, ws_bytes, group,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
+                            const float* rnV, const float* rnT, const float* num, const float* usq,
+                            const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
+                            void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::allpairs_bwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
+                             act, c, rnV, rnT, num, usq, dscores, static_cast<__nv_bfloat16*>(dV), dT, workspace,
+                             ws_bytes, group, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,304 @@
+"""Autograd wrappers over the clipk C ABI (include/clipk.h).
+
+The host side is PyTorch only for device memory, streams and autograd bookkeeping; all arithmetic on the hot
+path runs in the sm_100a kernels of libclipk.so.  There is no CPU / eager fallback: CPU tensors raise.
+
+Reference call sites (relative to the reference root, PACL = Patch-Aligned-Contrastive-Learning):
+  patch_alignment / forward     PACL/model/pacl.py:120-145 (copies :249-275, :341-365)
+  ClipLoss                      PACL/model/pacl.py:489-514
+  eval scoring                  PACL/eval_pacl.py:50-57, :303-309; PACL/eval_llm2pacl.py:62-67
+  open_clip ClipLoss            open_clip/src/open_clip/loss.py:89-193
+"""
+import torch
+
+from . import _lib
+
+ACT = {"sigmoid": 0, "sigmoid10": 0, "ones": 1}
+_DT = {torch.bfloat16: 0, torch.float32: 1}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.ClipkError("clip_embeds_b200 runs on B200 (CUDA) tensors only; there is no CPU fallback")
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+# --------------------------------------------------------------------------------------------- paired PACL
+def _paired_forward(V, T, act, want_act=False, want_cos=False):
+    _need_cuda(V, T)
+    if V.dtype not in _DT:
+        raise _lib.ClipkError(f"unsupported dtype {V.dtype} (bf16 or fp32)")
+    T = T.to(V.dtype)
+    V = V.contiguous()
+    T = T.contiguous()
+    Bv, P, D = V.shape
+    B = T.shape[0]
+    if Bv == B:
+        v_div = 1
+    elif B % Bv == 0:
+        v_div = B // Bv          # each image scored against B / Bv consecutive captions
+    else:
+        raise ValueError(f"images {Bv} and texts {B}: need equal batch or one image per K captions")
+    dev = V.device
+    img = _f32(B, D, device=dev)
+    txt = _f32(B, D, device=dev)
+    stats = _f32(B, 2, device=dev)
+    a = _f32(B, P, device=dev) if want_act else None
+    cos = _f32(B, device=dev) if want_cos else None
+    _lib.call("clipk_pacl_paired_fwd", V.data_ptr(), T.data_ptr(), _DT[V.dtype], B, v_div, P, D, act, _p(a),
+              img.data_ptr(), txt.data_ptr(), _p(cos), stats.data_ptr(), _stream())
+    return img, txt, stats, a, cos, V, T
+
+
+class _PaclPaired(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, T, act):
+        img, txt, stats, _, _, Vc, Tc = _paired_forward(V, T, act)
+        if Vc.shape[0] != Tc.shape[0]:
+            ctx.mark_non_differentiable(img, txt)
+        ctx.save_for_backward(Vc, Tc, img, stats)
+        ctx.act = act
+        ctx.t_dtype = T.dtype
+        return img, txt
+
+    @staticmethod
+    def backward(ctx, d_img, d_txt):
+        V, T, img, stats = ctx.saved_tensors
+        B, P, D = V.shape
+        d_img = d_img.float().contiguous()
+        d_txt = d_txt.float().contiguous() if d_txt is not None else None
+        dV = torch.empty_like(V)
+        dT = torch.empty_like(T)
+        _lib.call("clipk_pacl_paired_bwd", V.data_ptr(), T.data_ptr(), _DT[V.dtype], B, P, D, ctx.act, img.data_ptr(),
+                  stats.data_ptr(), d_img.data_ptr(), _p(d_txt), dV.data_ptr(), dT.data_ptr(), _stream())
+        return dV, dT.to(ctx.t_dtype), None
+
+
+def patch_alignment(visual_patch_proj, text_cls_proj):
+    """sigmoid(10 * cos(patch, text)) -> [B, P] fp32 (pacl.py:120-133).  Not differentiable on its own; use
+    `pacl_pool` for the training path (activation + pooling + normalisation fused, one pass over V)."""
+    return _paired_forward(visual_patch_proj, text_cls_proj, ACT["sigmoid"], want_act=True)[3]
+
+
+def pacl_pool(visual_proj, text_proj, activation="sigmoid"):
+    """PACL model forward after the projection heads (pacl.py:140-145 and variants): returns
+    (normalised text-conditioned pooled image feature [B,D], normalised text feature [B,D]) in fp32.
+    activation='ones' reproduces the checked-in "Eval only" forward (pacl.py:141-142)."""
+    return _PaclPaired.apply(visual_proj, text_proj, ACT[activation])
+
+
+def pacl_eval_scores(visual_proj, text_proj, c=100.0, activation="sigmoid"):
+    """Eval protocol (eval_pacl.py:50-57): `visual_proj` [items,P,D], `text_proj` [items,K,D] ->
+    diagonal scores [items,K] (= c * cos) and top-1 index [items] (fp32 arithmetic, no tensor cores)."""
+    items, K, D = text_proj.shape
+    cos = _paired_forward(visual_proj, text_proj.reshape(items * K, D), ACT[activation], want_cos=True)[4]
+    scores = (c * cos).reshape(items, K)
+    return scores, scores.argmax(dim=-1)
+
+
+# --------------------------------------------------------------------------------------------- all-pairs PACL
+def default_group(Bt, P, D, backward=True, budget_bytes=48 << 20):
+    ppad = (P + 63) // 64 * 64
+    per_image = Bt * ((4 * ppad * 2 + D * 2) if backward else ppad * 2)
+    return max(1, min(64, budget_bytes // max(per_image, 1)))
+
+
+class _PaclAllPairs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, T, c, act, group):
+        _need_cuda(V, T)
+        Vb = V.to(torch.bfloat16).contiguous()
+        Tb = T.to(torch.bfloat16).contiguous()
+        Bi, P, D = Vb.shape
+        Bt = Tb.shape[0]
+        dev = Vb.device
+        g = group or default_group(Bt, P, D, backward=False)
+        g = min(g, Bi)
+        rnV, rnT = _f32(Bi, P, device=dev), _f32(Bt, device=dev)
+        num, usq, scores = _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev)
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_pacl_allpairs_fwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
+                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), ws.data_ptr(), nbytes, g,
+                  _stream())
+        ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq)
+        ctx.cfg = (c, act, group, V.dtype, T.dtype)
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        Vb, Tb, rnV, rnT, num, usq = ctx.saved_tensors
+        c, act, group, v_dtype, t_dtype = ctx.cfg
+        Bi, P, D = Vb.shape
+        Bt = Tb.shape[0]
+        dev = Vb.device
+        g = group or default_group(Bt, P, D, backward=True)
+        g = min(g, Bi)
+        dscores = dscores.float().contiguous()
+        dV = torch.empty_like(Vb)
+        dT = _f32(Bt, D, device=dev)
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, 1)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_pacl_allpairs_bwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
+                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), dscores.data_ptr(), dV.data_ptr(), dT.data_ptr(),
+                  ws.data_ptr(), nbytes, g, _stream())
+        return dV.to(v_dtype), dT.to(t_dtype), None, None, None
+
+
+def pacl_scores(visual_proj, text_proj, c=1.0, activation="sigmoid", group=None):
+    """All-pairs text-conditioned scores [Bi,Bt] = c * cos(pool(V_i | t_k), t_k) (bf16 tensor cores, fp32
+    accumulation).  Inputs are cast to bf16; gradients come back in the input dtypes."""
+    return _PaclAllPairs.apply(visual_proj, text_proj, float(c), ACT[activation], group)
+
+
+# --------------------------------------------------------------------------------------------- CE on a score matrix
+def _merge_cols(col_max, col_sum, group=None):
+    """(max, sumexp) partial column statistics -> column LSE, merged across ranks when a group is given."""
+    if group is not None:
+        import torch.distributed as dist
+        W = dist.get_world_size(group)
+        both = torch.stack([col_max, col_sum])                          # [2, N]
+        gathered = [torch.empty_like(both) for _ in range(W)]
+        dist.all_gather(gathered, both, group=group)
+        allb = torch.stack(gathered)                                    # [W, 2, N]
+        gmax = allb[:, 0].max(dim=0).values
+        gsum = (allb[:, 1] * torch.exp(allb[:, 0] - gmax)).sum(dim=0)
+        return gmax + torch.log(gsum)
+    return col_max + torch.log(col_sum)
+
+
+class _ScoreInfoNCE(torch.autograd.Function):
+    """loss = 1/2 [ CE(L, arange) + CE(L^T, arange) ] for a score matrix L (pacl.py:509-512 applied to scores).
+
+    Image-sharded form: this rank holds rows [offset, offset + M) of the global [N, N] matrix; column statistics
+    are merged across ranks, and the returned loss is the GLOBAL loss (identical on every rank)."""
+
+    @staticmethod
+    def forward(ctx, L, offset, group):
+        _need_cuda(L)
+        L = L.float().contiguous()
+        M, N = L.shape
+        dev = L.device
+        row_lse, row_loss = _f32(M, device=dev), _f32(M, device=dev)
+        col_max, col_sum = _f32(N, device=dev), _f32(N, device=dev)
+        st = _stream()
+        _lib.call("clipk_ce_rows", L.data_ptr(), M, N, N, 0, offset, row_lse.data_ptr(), row_loss.data_ptr(), st)
+        _lib.call("clipk_ce_cols", L.data_ptr(), M, N, N, col_max.data_ptr(), col_sum.data_ptr(), st)
+        col_lse = _merge_cols(col_max, col_sum, group)
+        diag = row_lse - row_loss                                        # L[i, i + offset]
+        part = torch.stack([row_loss.sum(), (col_lse[offset:offset + M] - diag).sum()])
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(part, group=group)
+        loss = 0.5 * (part[0] + part[1]) / N
+        dL = torch.empty_like(L)
+        _lib.call("clipk_ce_scores_grad", L.data_ptr(), M, N, N, row_lse.data_ptr(), col_lse.data_ptr(), offset,
+                  0.5 / N, 0.5 / N, dL.data_ptr(), st)
+        ctx.save_for_backward(dL)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dL,) = ctx.saved_tensors
+        return dL * g, None, None
+
+
+def score_infonce(scores, offset=0, group=None):
+    return _ScoreInfoNCE.apply(scores, int(offset), group)
+
+
+# --------------------------------------------------------------------------------------------- CE from features
+class _FeatRowCE(torch.autograd.Function):
+    """sum over valid rows of CE(scale * X Y^T + bias, labels) and the number of valid rows.
+
+    bf16 inputs run on the tcgen05 engine (logits never materialised); fp32 inputs run the fp32 SIMT path."""
+
+    @staticmethod
+    def forward(ctx, X, Y, scale, bias, labels, label_offset):
+        _need_cuda(X, Y)
+        M, D = X.shape
+        N = Y.shape[0]
+        dev = X.device
+        st = _stream()
+        row_lse, row_loss = _f32(M, device=dev), _f32(M, device=dev)
+        lab_ptr = 0
+        if labels is not None:
+            labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+            lab_ptr = labels.data_ptr()
+            valid = (labels >= 0)
+        else:
+            valid = torch.ones(M, dtype=torch.bool, device=dev)
+        ctx.scale_needs_grad = torch.is_tensor(scale) and scale.requires_grad
+        sc = float(scale)        # NOTE: a device scalar costs one host sync here
+        bi = float(bias) if bias is not None else 0.0
+        if X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16:
+            Xc, Yc = X.contiguous(), Y.contiguous()
+            nbytes = _lib.lib().clipk_ce_feat_workspace_bytes(M, N)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("clipk_ce_feat_fwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
+                      row_lse.data_ptr(), row_loss.data_ptr(), ws.data_ptr(), nbytes, st)
+            ctx.ws = ws
+            logits = None
+        else:
+            Xc, Yc = X.float().contiguous(), Y.float().contiguous()
+            logits = _f32(M, N, device=dev)
+            if bi != 0.0:
+                logits.fill_(bi)
+            _lib.call("clipk_sgemm_f32", Xc.data_ptr(), D, 1, Yc.data_ptr(), 1, D, logits.data_ptr(), N, M, N, D, sc,
+                      1.0 if bi != 0.0 else 0.0, st)
+            _lib.call("clipk_ce_rows", logits.data_ptr(), M, N, N, lab_ptr, label_offset, row_lse.data_ptr(),
+                      row_loss.data_ptr(), st)
+            ctx.ws = None
+        ctx.save_for_backward(Xc, Yc, row_lse, labels if labels is not None else torch.empty(0, device=dev), valid,
+                              logits if logits is not None else torch.empty(0, device=dev))
+        ctx.cfg = (sc, bi, labels is not None, label_offset, X.dtype, Y.dtype)
+        loss_sum = (row_loss * valid).sum()
+        ctx.mark_non_differentiable(valid)
+        return loss_sum, valid
+
+    @staticmethod
+    def backward(ctx, g_sum, _g_valid):
+        Xc, Yc, row_lse, labels, valid, logits = ctx.saved_tensors
+        sc, bi, has_labels, label_offset, xdt, ydt = ctx.cfg
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        dev = Xc.device
+        st = _stream()
+        lab_ptr = labels.data_ptr() if has_labels else 0
+        row_w = (valid.float() * g_sum.float()).contiguous()
+        dX, dY = _f32(M, D, device=dev), _f32(N, D, device=dev)
+        if Xc.dtype == torch.bfloat16:
+            ws = ctx.ws
+            _lib.call("clipk_ce_feat_bwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
+                      row_lse.data_ptr(), row_w.data_ptr(), dX.data_ptr(), 0, dY.data_ptr(), 0, ws.data_ptr(),
+                      ws.numel(), st)
+        else:
+            dL = torch.empty_like(logits)
+            _lib.call("clipk_ce_rows_grad", logits.data_ptr(), M, N, N, row_lse.data_ptr(), lab_ptr, label_offset,
+                      row_w.data_ptr(), dL.data_ptr(), st)
+            # dX = scale * dL Y ; dY = scale * dL^T X
+            _lib.call("clipk_sgemm_f32", dL.data_ptr(), N, 1, Yc.data_ptr(), D, 1, dX.data_ptr(), D, M, D, N, sc, 0.0, st)
+            _lib.call("clipk_sgemm_f32", dL.data_ptr(), 1, N, Xc.data_ptr(), D, 1, dY.data_ptr(), D, N, D, M, sc, 0.0, st)
+        dscale = None
+        if ctx.scale_needs_grad:      # d/dscale sum(dlogits * x.y) = <dX, X> / scale
+            dscale = (dX * Xc.float()).sum() / sc
+        return dX.to(xdt), dY.to(ydt), dscale, None, None, None
+
+
+def feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0):
+    """Mean over non-ignored rows of cross_entropy(scale * X @ Y.T + bias, labels)  (F.cross_entropy semantics,
+    ignore_index = any negative label).  labels=None means label_i = i + label_offset."""
+    loss_sum, valid = _FeatRowCE.apply(X, Y, scale, bias, labels, int(label_offset))
+    return loss_sum / valid.sum().clamp_min(1)

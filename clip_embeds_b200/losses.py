@@ -1,0 +1,105 @@
+"""Drop-in loss modules with the reference's constructor and call signatures.
+
+  ClipLoss(temperature)(image_features, text_features)                      PACL/model/pacl.py:489-514
+  OpenClipLoss(local_loss, gather_with_grad, cache_labels, rank, world_size, use_horovod, usehardtext)
+      (image_features, text_features, logit_scale, logit_bias=None, output_dict=False)
+                                                                            open_clip/src/open_clip/loss.py:89-193
+  PaclAllPairsLoss(temperature)(visual_proj, text_proj)                     north_star all-pairs InfoNCE
+      (reference: per-image eval loop + pacl.py:509-512)
+"""
+import torch
+import torch.nn as nn
+
+from . import dist as cdist
+from . import functional as Fk
+
+
+class ClipLoss(nn.Module):
+    """Symmetric InfoNCE with fixed logit scale 1/temperature (pacl.py:489-514)."""
+
+    def __init__(self, temperature):
+        super().__init__()
+        self.logit_scale = 1.0 / temperature
+
+    def forward(self, image_features, text_features):
+        li = Fk.feat_row_ce(image_features, text_features, self.logit_scale)
+        lt = Fk.feat_row_ce(text_features, image_features, self.logit_scale)
+        return (li + lt) / 2
+
+
+class PaclAllPairsLoss(nn.Module):
+    """InfoNCE over the all-pairs text-conditioned score matrix; image-sharded across `group` ranks.
+
+    forward(visual_proj [b,P,D] (this rank's images), text_proj [b,D] (this rank's captions)) -> global loss.
+    Texts are all-gathered (with gradient: reduce-scatter in backward), V never moves."""
+
+    def __init__(self, temperature=0.1, activation="sigmoid", group=None, image_group=None):
+        super().__init__()
+        self.logit_scale = 1.0 / temperature
+        self.activation = activation
+        self.group = group
+        self.image_group = image_group
+
+    def forward(self, visual_proj, text_proj):
+        pg = self.group
+        if pg is not None and cdist.world_size(pg) > 1:
+            all_text = cdist.all_gather_with_grad(text_proj, pg)
+            offset = cdist.rank(pg) * visual_proj.shape[0]
+        else:
+            pg = None
+            all_text = text_proj
+            offset = 0
+        scores = Fk.pacl_scores(visual_proj, all_text, self.logit_scale, self.activation, self.image_group)
+        return Fk.score_infonce(scores, offset, pg)
+
+
+class OpenClipLoss(nn.Module):
+    """open_clip ClipLoss incl. the fork's left/right hard-negative texts (`usehardtext`), loss.py:89-193.
+
+    text_features holds the rank's B original captions followed by its H_r hard negatives (collate layout,
+    open_clip_train/data.py:122-134).  Horovod is not supported (as in the reference's diffsize gather)."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False, usehardtext=False, group=None):
+        super().__init__()
+        if use_horovod:
+            raise NotImplementedError("horovod gather is not supported (reference: loss.py:76)")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.usehardtext = usehardtext
+        self.group = group
+
+    def forward(self, image_features, text_features, logit_scale, logit_bias=None, output_dict=False):
+        b = image_features.shape[0]
+        bias = 0.0 if logit_bias is None else logit_bias
+        if self.world_size > 1:
+            if self.usehardtext:
+                assert self.gather_with_grad, "usehardtext requires gather_with_grad (loss.py:77)"
+            all_img, all_txt = cdist.gather_features(image_features, text_features, b, self.usehardtext,
+                                                     self.gather_with_grad, self.local_loss, self.rank,
+                                                     self.world_size, self.group)
+            if self.local_loss:
+                off = b * self.rank
+                li = Fk.feat_row_ce(image_features, all_txt, logit_scale, bias, None, off)
+                n_txt = text_features.shape[0]
+                lab_t = torch.full((n_txt,), -100, dtype=torch.int64, device=text_features.device)
+                lab_t[:b] = torch.arange(b, device=text_features.device) + off
+                lt = Fk.feat_row_ce(text_features, all_img, logit_scale, bias, lab_t, 0)
+            else:
+                N = all_img.shape[0]
+                li = Fk.feat_row_ce(all_img, all_txt, logit_scale, bias, None, 0)
+                lab_t = torch.full((all_txt.shape[0],), -100, dtype=torch.int64, device=all_txt.device)
+                lab_t[:N] = torch.arange(N, device=all_txt.device)
+                lt = Fk.feat_row_ce(all_txt, all_img, logit_scale, bias, lab_t, 0)
+        else:
+            li = Fk.feat_row_ce(image_features, text_features, logit_scale, bias, None, 0)
+            n_txt = text_features.shape[0]
+            lab_t = torch.full((n_txt,), -100, dtype=torch.int64, device=text_features.device)
+            lab_t[:b] = torch.arange(b, device=text_features.device)
+            lt = Fk.feat_row_ce(text_features, image_features, logit_scale, bias, lab_t, 0)
+        total = (li + lt) / 2
+        return {"contrastive_loss": total} if output_dict else total

@@ -52,6 +52,75 @@ int clipk_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const
                     int64_t strideB, void* C, int64_t ldc, int64_t strideC, int out_dtype, int M, int N, int K,
                     int batches, float alpha, int accumulate, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * PACL paired path (reference training / eval semantics; HBM-bound, one pass over V per direction).
+ *   V [B / v_div, P, D], T [B, D] (dtype CLIPK_BF16 | CLIPK_F32).  Sample b uses image b / v_div
+ *   (v_div = 1: paired batch; v_div = K: one image scored against K captions, eval_pacl.py:50-57).
+ *   act_out [B,P] (nullable) = sigmoid(10 cos)            -> patch_alignment, pacl.py:120-133
+ *   img_feat [B,D] = n(sum_p a_p V_p), txt_feat [B,D] = n(T) -> forward, pacl.py:140-145 (a := 1 for CLIPK_ACT_ONES)
+ *   cosine [B] (nullable) = <img_feat, txt_feat>           -> diagonal of eval_pacl.py:56
+ *   stats [B,2] = (||u||, ||t||), saved for backward.
+ * Backward: d_img, d_txt [B,D] fp32 (d_txt nullable) -> dV [B,P,D], dT [B,D] in the input dtype.
+ */
+int clipk_pacl_paired_fwd(const void* V, const void* T, int dtype, int B, int v_div, int P, int D, int act,
+                          float* act_out, float* img_feat, float* txt_feat, float* cosine, float* stats,
+                          void* stream);
+int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P, int D, int act,
+                          const float* img_feat, const float* stats, const float* d_img, const float* d_txt,
+                          void* dV, void* dT, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * PACL all-pairs text-conditioned scores (north_star (1)-(3); reference: the eval call model(img_i, texts) of
+ * eval_pacl.py:53-57, :303-309 looped over images; patch_alignment pacl.py:120-133; pooling pacl.py:143-145).
+ *   V bf16 [Bi,P,D], T bf16 [Bt,D]  ->  scores fp32 [Bi,Bt] = c * < n(sum_p sigmoid(10 s_ikp) V_ip), n(t_k) >
+ * Saved for backward (caller-owned): rnV [Bi,P], rnT [Bt], num [Bi,Bt], usq [Bi,Bt].  The [Bi,Bt,P] activations
+ * only ever exist for `group` images at a time inside `workspace` (tcgen05 GEMMs with fused epilogues).
+ * Backward: dscores [Bi,Bt] -> dV bf16 [Bi,P,D], dT fp32 [Bt,D] (gradient w.r.t. the raw T).
+ */
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int backward);
+int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
+                            float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
+                            int group, void* stream);
+int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
+                            const float* rnV, const float* rnT, const float* num, const float* usq,
+                            const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Cross-entropy over a materialised fp32 matrix L [M,N] (leading dim ld): F.cross_entropy at pacl.py:509-512,
+ * loss.py:188-191.  label of row i = labels[i] (nullable) or i + label_offset; labels < 0 are ignored rows.
+ *   clipk_ce_rows       : row_lse [M], row_loss [M] (= lse - L[i,label], 0 for ignored rows; nullable)
+ *   clipk_ce_cols       : per-column (max, sum exp(L - max)) over the M local rows (merge across ranks, then log)
+ *   clipk_ce_scores_grad: dL = w_row (softmax_row - onehot) + w_col (softmax_col - onehot), label = i + offset
+ *   clipk_ce_rows_grad  : dL = row_w[i] (softmax_row - onehot) with explicit labels
+ */
+int clipk_ce_rows(const float* L, int M, int N, int64_t ld, const int64_t* labels, int64_t label_offset,
+                  float* row_lse, float* row_loss, void* stream);
+int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, float* col_sum, void* stream);
+int clipk_ce_scores_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const float* col_lse,
+                         int64_t label_offset, float w_row, float w_col, float* dL, void* stream);
+int clipk_ce_rows_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const int64_t* labels,
+                       int64_t label_offset, const float* row_w, float* dL, void* stream);
+
+/* fp32 GEMM with generic strides (fp32 feature path: `logit_scale * x @ y.T`, pacl.py:499-500, loss.py:156-164):
+ *   C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + beta * C[m*ldc + n] */
+int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                    int64_t ldc, int M, int N, int K, float alpha, float beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * bf16 feature cross-entropy on the tcgen05 engine (NegCLIP ClipLoss, loss.py:137-193; PACL ClipLoss, pacl.py:489-514):
+ *   logits = scale * X Y^T + bias, X bf16 [M,D], Y bf16 [N,D]; the [M,N] logits are never written.
+ *   fwd: row_lse [M], row_loss [M].   bwd: row_w [M] (upstream / #valid rows; 0 for ignored rows)
+ *        dX [M,D] / dY [N,D] fp32 (nullable; acc* != 0 accumulates into the buffer).
+ */
+size_t clipk_ce_feat_workspace_bytes(int M, int N);
+int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                      const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
+                      size_t ws_bytes, void* stream);
+int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                      const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
+                      int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

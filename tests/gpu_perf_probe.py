@@ -1,0 +1,73 @@
+"""Quick perf probe (diagnostic, not the bench): engine GEMM TFLOP/s and all-pairs fwd/bwd times."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from clip_embeds_b200 import _lib  # noqa: E402
+import clip_embeds_b200.functional as Fk  # noqa: E402
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    return min(ts), sum(ts) / len(ts)
+
+
+def gemm(M, N, K, nb=1, a_mn=0, b_mn=0):
+    A = torch.randn(nb, M, K, device="cuda").to(torch.bfloat16)
+    B = torch.randn(nb, N, K, device="cuda").to(torch.bfloat16)
+    Ad = A.transpose(1, 2).contiguous() if a_mn else A
+    Bd = B.transpose(1, 2).contiguous() if b_mn else B
+    C = torch.empty(nb, M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _lib.call("clipk_gemm_bf16", Ad.data_ptr(), a_mn, M if a_mn else K, M * K, Bd.data_ptr(), b_mn, N if b_mn else K,
+                  N * K, C.data_ptr(), N, M * N, 0, M, N, K, nb, 1.0, 0, st)
+    mn, av = timeit(run)
+    fl = 2.0 * M * N * K * nb
+    print(f"gemm M={M} N={N} K={K} nb={nb} a_mn={a_mn} b_mn={b_mn}: {mn:.3f} ms  {fl / mn / 1e9:.1f} TFLOP/s", flush=True)
+    t0 = timeit(lambda: torch.matmul(A, B.transpose(1, 2)))[0]
+    print(f"   cuBLAS (torch.matmul) same shape: {t0:.3f} ms {fl / t0 / 1e9:.1f} TFLOP/s", flush=True)
+
+
+def allpairs(B, P, D, group=None):
+    V = torch.randn(B, P, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    T = torch.randn(B, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    g = torch.randn(B, B, device="cuda") / B
+
+    def fwd():
+        with torch.no_grad():
+            Fk.pacl_scores(V, T, 10.0, "sigmoid", group)
+
+    def fb():
+        V.grad = None
+        T.grad = None
+        s = Fk.pacl_scores(V, T, 10.0, "sigmoid", group)
+        s.backward(g)
+    tf = timeit(fwd, 3, 1)[0]
+    tb = timeit(fb, 3, 1)[0]
+    fl = 12.0 * B * B * P * D
+    print(f"allpairs B={B} P={P} D={D} group={group}: fwd {tf:.2f} ms ({4.0*B*B*P*D/tf/1e9:.0f} TF/s) fwd+bwd {tb:.2f} ms "
+          f"-> {B / tb * 1e3:.0f} pairs/s, {fl / tb / 1e9:.0f} TFLOP/s algorithmic", flush=True)
+
+
+if __name__ == "__main__":
+    gemm(4096, 4096, 4096)
+    gemm(8192, 8192, 768)
+    gemm(1024, 576, 768, nb=16)
+    gemm(1024, 768, 576, nb=16, b_mn=1)
+    gemm(576, 768, 1024, nb=16, a_mn=1, b_mn=1)
+    for grp in (4, 8, 16):
+        allpairs(1024, 576, 768, grp)

@@ -1,0 +1,72 @@
+"""GPU parity: cross-entropy paths (fp32 SIMT, bf16 tcgen05 engine) vs the oracle / reference goldens."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_openclip_hardneg_fp32_golden(goldens):
+    from clip_embeds_b200.losses import OpenClipLoss
+    G = goldens["G3"]
+    img = O.l2n(O.rn(5, 8, 16)).cuda().requires_grad_()
+    txt = O.l2n(O.rn(6, 11, 16)).cuda().requires_grad_()
+    loss = OpenClipLoss(usehardtext=True)(img, txt, torch.tensor(100.0))
+    loss.backward()
+    assert abs(loss.item() - G["loss"].item()) < 1e-4 * G["loss"].item()
+    assert rel_l2(img.grad.cpu(), G["dimg"]) < 1e-4
+    assert rel_l2(txt.grad.cpu(), G["dtxt"]) < 1e-4
+    img = O.l2n(O.rn(5, 8, 16)).cuda().requires_grad_()
+    txt = O.l2n(O.rn(6, 8, 16)).cuda().requires_grad_()
+    out = OpenClipLoss()(img, txt, torch.tensor(20.0), logit_bias=torch.tensor(-3.0), output_dict=True)
+    out["contrastive_loss"].backward()
+    assert abs(out["contrastive_loss"].item() - G["loss_plain"].item()) < 1e-5 * max(1, G["loss_plain"].item())
+    assert rel_l2(img.grad.cpu(), G["dimg_plain"]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(8, 11, 16), (300, 700, 256), (1024, 1300, 768)])
+def test_openclip_hardneg_bf16_engine(shape):
+    """bf16 tensor-core CE vs fp32 oracle on the same bf16-rounded features.  Tolerance: loss 2e-3 rel,
+    gradients 2e-2 rel-L2 (dL is stored in bf16 before the two gradient GEMMs)."""
+    from clip_embeds_b200.losses import OpenClipLoss
+    B, Nt, D = shape
+    ib = O.l2n(O.rn(51, B, D)).to(torch.bfloat16)
+    tb = O.l2n(O.rn(52, Nt, D)).to(torch.bfloat16)
+    io = ib.float().requires_grad_()
+    to = tb.float().requires_grad_()
+    lo = O.openclip_loss_single(io, to, 30.0, usehardtext=True)
+    lo.backward()
+    img = ib.cuda().requires_grad_()
+    txt = tb.cuda().requires_grad_()
+    scale = torch.tensor(30.0, device="cuda", requires_grad=True)
+    loss = OpenClipLoss(usehardtext=True)(img, txt, scale)
+    loss.backward()
+    print(f"ce bf16 {shape}: loss {loss.item():.6f} vs {lo.item():.6f} rel_dimg {rel_l2(img.grad.float().cpu(), io.grad):.3e} "
+          f"rel_dtxt {rel_l2(txt.grad.float().cpu(), to.grad):.3e}")
+    assert abs(loss.item() - lo.item()) < 2e-3 * max(1.0, abs(lo.item()))
+    assert rel_l2(img.grad.float().cpu(), io.grad) < 2e-2
+    assert rel_l2(txt.grad.float().cpu(), to.grad) < 2e-2
+    # d loss / d logit_scale
+    so = torch.tensor(30.0, requires_grad=True)
+    O.openclip_loss_single(ib.float(), tb.float(), so, usehardtext=True).backward()
+    assert abs(scale.grad.item() - so.grad.item()) < 2e-2 * max(1e-3, abs(so.grad.item())) + 1e-5
+
+
+def test_pacl_cliploss_bf16():
+    from clip_embeds_b200.losses import ClipLoss
+    B, D = 512, 768
+    ib = O.l2n(O.rn(61, B, D)).to(torch.bfloat16)
+    tb = O.l2n(O.rn(62, B, D)).to(torch.bfloat16)
+    io = ib.float().requires_grad_()
+    to = tb.float().requires_grad_()
+    lo = O.pacl_clip_loss(io, to, 0.1)
+    lo.backward()
+    img = ib.cuda().requires_grad_()
+    txt = tb.cuda().requires_grad_()
+    loss = ClipLoss(0.1)(img, txt)
+    loss.backward()
+    assert abs(loss.item() - lo.item()) < 2e-3 * abs(lo.item())
+    assert rel_l2(img.grad.float().cpu(), io.grad) < 2e-2
+    assert rel_l2(txt.grad.float().cpu(), to.grad) < 2e-2
