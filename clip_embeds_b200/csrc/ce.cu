@@ -160,7 +160,7 @@ namespace epi {
 // per-(row, n-tile) online log-sum-exp partial of logits = scale * acc + bias; captures the label logit.
 struct LsePart {
   struct Params {
-    float2* part;            // [M][tiles_n] (max, sumexp)
+    float2* part;            // [M][tiles_n] (max, sumexp); tiles_n counts HALF tiles (two epilogue warps per row)
     float* pos;              // [M] logit at the label column (written by the tile that owns it)
     const int64_t* labels;   // nullable
     int64_t label_offset;
@@ -200,8 +200,8 @@ struct LsePart {
       p.pos[m] = pv;
     }
   }
-  __device__ void tile_end(int, int m, int, int tn) {
-    if (m < p.M) p.part[(int64_t)m * p.tiles_n + tn] = make_float2(mx, sm);
+  __device__ void tile_end(int, int m, int, int tn, int half) {
+    if (m < p.M) p.part[(int64_t)m * p.tiles_n + 2 * tn + half] = make_float2(mx, sm);
   }
 };
 
@@ -238,7 +238,7 @@ struct DlOut {
     }
     store_bf16x32(p.dL + (int64_t)m * p.ldd + n, v, min(32, p.N - n));
   }
-  __device__ void tile_end(int, int, int, int) {}
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 }  // namespace epi
@@ -278,7 +278,7 @@ static size_t ce_carve(CeWorkspace* w, void* base, int M, int N) {
     off += (bytes + 1023) / 1024 * 1024;
     return p;
   };
-  const int tiles_n = (N + 255) / 256;
+  const int tiles_n = 2 * ((N + 255) / 256);
   const int mc = M < kCeChunkRows ? M : kCeChunkRows;
   w->part = static_cast<float2*>(take((size_t)M * tiles_n * sizeof(float2)));
   w->pos = static_cast<float*>(take((size_t)M * 4));
@@ -297,7 +297,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   a.ptr = X; a.rows = M; a.k = D; a.ld = D;
   b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
   const int ks[1] = {(D + 63) / 64};
-  const int tiles_n = (N + 255) / 256;
+  const int tiles_n = 2 * ((N + 255) / 256);   // one partial per (n-tile, epilogue-warp half)
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
   epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
   CLIPK_TRY(launch_gemm<256, false, false, epi::LsePart>(&a, &b, 1, ks, ks, M, N, 1, ep, st));

@@ -57,6 +57,8 @@ struct OperandDesc {
   int64_t batch_stride = 0;  // elements
   int bmul = 0;              // batch coordinate = b * bmul + sub * smul
   int smul = 0;
+  int sub_per_batch = 0;     // split-K: sub = b * sub_per_batch + (kstep / ksub)
+  int sub_total = 0;         // >0: uneven split, batch b covers sub-batches [b*spb, min((b+1)*spb, sub_total))
 };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -78,6 +80,8 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
     pb.ksub[q] = ksub[q] > 0 ? ksub[q] : (ksteps[q] > 0 ? ksteps[q] : 1);
     pb.a_bmul[q] = a[q].bmul; pb.a_smul[q] = a[q].smul;
     pb.b_bmul[q] = b[q].bmul; pb.b_smul[q] = b[q].smul;
+    pb.sub_per_batch[q] = a[q].sub_per_batch;
+    pb.sub_total[q] = a[q].sub_total;
     if (!A_MN) {
       CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].k, a[q].rows, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, eng::BM));
     } else {

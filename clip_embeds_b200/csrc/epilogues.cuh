@@ -91,7 +91,7 @@ struct Store {
       }
     }
   }
-  __device__ void tile_end(int, int, int, int) {}
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 }  // namespace epi
@@ -138,54 +138,86 @@ __device__ __forceinline__ void load_f16x32(const __half* src, float* v, int val
   }
 }
 
-__device__ __forceinline__ float fast_sigmoid10(float s) { return __frcp_rn(1.f + __expf(-10.f * s)); }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+// sigmoid(10 s) = 0.5 tanh(5 s) + 0.5 : one MUFU (tanh.approx.f32, rel. error ~2^-11, far below the bf16 rounding
+// the activation receives before it is used as an MMA operand)
+__device__ __forceinline__ float fast_sigmoid10(float s) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(5.f * s));
+  return fmaf(0.5f, t, 0.5f);
+}
+// round-to-nearest-even to bf16 precision with integer ALU ops (finite inputs), result kept as fp32
+__device__ __forceinline__ float bf16_round(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xFFFF0000u);
+}
+// store 32 fp32 values that are ALREADY bf16-representable: pack the high halves with PRMT (no conversion)
+__device__ __forceinline__ void store_bf16x32_exact(__nv_bfloat16* dst, const float* v, int valid) {
+  if (valid >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = __byte_perm(__float_as_uint(v[8 * j + 0]), __float_as_uint(v[8 * j + 1]), 0x7632);
+      u.y = __byte_perm(__float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]), 0x7632);
+      u.z = __byte_perm(__float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]), 0x7632);
+      u.w = __byte_perm(__float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]), 0x7632);
+      d4[j] = u;
+    }
+  } else {
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dst[j] = __float2bfloat16(v[j]);
+  }
+}
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1
 // acc[m=text k][n=patch p] = <T_k, V_ip> (raw).  s = acc * rnT[k] * rnV[i,p];  a = sigmoid(10 s)  (pacl.py:133)
 // writes A (bf16, zero in the pad columns), optionally S (fp16), and num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
+template <bool WITH_S>
 struct PaclAct {
   struct Params {
     const float* rnV;   // [batch][P]
     const float* rnT;   // [M]
     __nv_bfloat16* A;   // [batch][M][Ppad]
-    __half* S;          // [batch][M][Ppad] or nullptr
+    __half* S;          // [batch][M][Ppad] (WITH_S only)
     float* num;         // [batch][M] or nullptr
     int M, P, Ppad, act;
   };
   Params p;
-  float rt, acc;
-  __device__ explicit PaclAct(const Params& pp) : p(pp), rt(0.f), acc(0.f) {}
+  float rt, rt5, acc;
+  __device__ explicit PaclAct(const Params& pp) : p(pp), rt(0.f), rt5(0.f), acc(0.f) {}
   __device__ void tile_begin(int, int m, int) {
     acc = 0.f;
     rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
+    rt5 = 5.f * rt;
   }
   __device__ void chunk(int b, int m, int n, float* v) {
-    if (m >= p.M || n >= p.Ppad) return;
-    const float* rn = p.rnV + (int64_t)b * p.P;
-    float s[32];
+    if (n >= p.Ppad) return;                       // warp-uniform
+    const int lane = (int)ptx::lane_id();
+    // one coalesced load of the 32 patch norms of this chunk, broadcast by shuffle (branch-free inner loop)
+    const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+    const bool ones = p.act == CLIPK_ACT_ONES;
+    float s[WITH_S ? 32 : 1];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int pp = n + j;
-      if (pp < p.P) {
-        const float r = v[j] * rt;
-        const float sj = r * __ldg(rn + pp);
-        const float a = (p.act == CLIPK_ACT_ONES) ? 1.f : bf16_round(fast_sigmoid10(sj));
-        acc = fmaf(a, r, acc);
-        v[j] = a;
-        s[j] = sj;
-      } else {
-        v[j] = 0.f;
-        s[j] = 0.f;
-      }
+      const float rnj = __shfl_sync(0xffffffffu, rn_l, j);
+      const float x = v[j] * rnj;                  // <T_k, V_p> / |V_p|   (score = x * rnT)
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * rt5));
+      float a = ones ? 1.f : bf16_round(fmaf(0.5f, t, 0.5f));
+      a = (n + j < p.P) ? a : 0.f;
+      acc = fmaf(a, v[j], acc);                    // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
+      if constexpr (WITH_S) s[j] = x * rt;
+      v[j] = a;
     }
+    if (m >= p.M) return;
     const int valid = min(32, p.Ppad - n);
     const int64_t off = ((int64_t)b * p.M + m) * p.Ppad + n;
-    store_bf16x32(p.A + off, v, valid);
-    if (p.S != nullptr) store_f16x32(p.S + off, s, valid);
+    store_bf16x32_exact(p.A + off, v, valid);
+    if constexpr (WITH_S) store_f16x32(p.S + off, s, valid);
   }
-  __device__ void tile_end(int b, int m, int, int) {
-    if (p.num != nullptr && m < p.M) atomicAdd(p.num + (int64_t)b * p.M + m, acc);
+  __device__ void tile_end(int b, int m, int, int, int) {
+    if (p.num != nullptr && m < p.M) atomicAdd(p.num + (int64_t)b * p.M + m, acc * rt);
   }
 };
 
@@ -206,7 +238,7 @@ struct Usq {
     for (int j = 0; j < 32; ++j)
       if (n + j < p.N) acc = fmaf(v[j], v[j], acc);
   }
-  __device__ void tile_end(int b, int m, int, int) {
+  __device__ void tile_end(int b, int m, int, int, int) {
     if (m < p.M) atomicAdd(p.usq + (int64_t)b * p.M + m, acc);
   }
 };
@@ -240,7 +272,7 @@ struct GOut {
     for (int j = 0; j < 32; ++j) v[j] = al * t[j] - be * v[j];
     store_bf16x32(p.G + ((int64_t)b * p.M + m) * p.N + n, v, valid);
   }
-  __device__ void tile_end(int, int, int, int) {}
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM3 (bwd)
@@ -270,29 +302,23 @@ struct DsOut {
   __device__ void chunk(int b, int m, int n, float* v) {
     if (n >= p.Ppad) return;     // warp-uniform
     const bool row_ok = m < p.M;
+    const int lane = (int)ptx::lane_id();
     const int valid = min(32, p.Ppad - n);
     const int64_t off = ((int64_t)b * p.M + (row_ok ? m : 0)) * p.Ppad + n;
     float a[32], s[32];
-    if (row_ok) {
-      load_bf16x32(p.A + off, a, valid);
-      load_f16x32(p.S + off, s, valid);
-    }
-    const float* rn = p.rnV + (int64_t)b * p.P;
+    load_bf16x32(p.A + off, a, valid);             // rows >= M re-read row 0 (masked below)
+    load_f16x32(p.S + off, s, valid);
+    const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+    const float gate = (row_ok && p.act != CLIPK_ACT_ONES) ? 10.f : 0.f;
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int pp = n + j;
-      if (row_ok && pp < p.P) {
-        const float ds = (p.act == CLIPK_ACT_ONES) ? 0.f : v[j] * 10.f * a[j] * (1.f - a[j]);
-        const float dsv = ds * __ldg(rn + pp);
-        e[j] = fmaf(al, a[j], dsv);
-        v[j] = dsv * rt;
-        s[j] = ds * s[j];
-      } else {
-        e[j] = 0.f;
-        v[j] = 0.f;
-        s[j] = 0.f;
-      }
+      const float rnj = __shfl_sync(0xffffffffu, rn_l, j);      // 0 for p >= P: masks the pad columns
+      const float ds = v[j] * gate * a[j] * (1.f - a[j]);
+      const float dsv = ds * rnj;
+      e[j] = (n + j < p.P) ? fmaf(al, a[j], dsv) : 0.f;
+      v[j] = dsv * rt;
+      s[j] = (n + j < p.P) ? ds * s[j] : 0.f;
     }
     if (row_ok) {
       store_bf16x32(p.DS + off, v, valid);
@@ -302,7 +328,7 @@ struct DsOut {
     const int col = n + (int)ptx::lane_id();
     if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
   }
-  __device__ void tile_end(int, int, int, int) {}
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, dV (bwd)
@@ -334,7 +360,7 @@ struct DvOut {
     for (int j = 0; j < 32; ++j) v[j] = fmaf(-coef, x[j], v[j]);
     store_bf16x32(p.dV + off, v, valid);
   }
-  __device__ void tile_end(int, int, int, int) {}
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 }  // namespace epi

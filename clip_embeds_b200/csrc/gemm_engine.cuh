@@ -8,7 +8,9 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B tiles, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=16)
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator buffers of BN<=256 columns)
-//   warps 4..7  : epilogue       (tcgen05.ld 32x32b.x32; warp w owns TMEM lanes 32*(w%4)..+31)
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32; warp w owns TMEM lanes 32*(w%4)..+31; the two warps of a
+//                                 quadrant take alternate 32-column chunks, so each SMSP has two epilogue warps
+//                                 in flight to hide TMEM / global-load latency)
 //
 // Operands may be K-major (k contiguous in global memory: tensor map dims (k, row, batch)) or MN-major (row index
 // contiguous: tensor map dims (row, k, batch)); both land in shared memory as 128-byte swizzled rows, see
@@ -20,8 +22,9 @@ namespace eng {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps (2 per TMEM lane quadrant / SMSP)
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
 
 struct OperandMaps {
   CUtensorMap a[2];
@@ -37,6 +40,8 @@ struct Problem {
   int ksub[2];         // BK-steps per "sub-batch" (k index folds a second batch index; = ksteps when unused)
   int a_bmul[2], a_smul[2];  // A batch coordinate = b * a_bmul + sub * a_smul
   int b_bmul[2], b_smul[2];
+  int sub_per_batch[2];      // split-K over sub-batches: sub index = b * sub_per_batch + ks / ksub
+  int sub_total[2];          // >0: batch b only covers sub-batches [b*spb, min((b+1)*spb, sub_total)) (uneven split)
 };
 
 template <int BN>
@@ -48,6 +53,13 @@ struct SmemLayout {
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
 };
+
+__device__ __forceinline__ int ksteps_of(const Problem& pb, int q, int b) {
+  if (pb.sub_total[q] <= 0) return pb.ksteps[q];
+  int subs = pb.sub_total[q] - b * pb.sub_per_batch[q];
+  subs = subs < pb.sub_per_batch[q] ? subs : pb.sub_per_batch[q];
+  return (subs > 0 ? subs : 0) * pb.ksub[q];
+}
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -80,7 +92,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], kEpiWarps);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -104,9 +116,11 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
         const int m0 = (rem / pb.tiles_n) * BM;
         const int n0 = (rem % pb.tiles_n) * BN;
         for (int q = 0; q < pb.num_pairs; ++q) {
-          for (int ks = 0; ks < pb.ksteps[q]; ++ks) {
-            const int sub = ks / pb.ksub[q];
-            const int k0 = (ks - sub * pb.ksub[q]) * BK;
+          const int nks = ksteps_of(pb, q, b);
+          for (int ks = 0; ks < nks; ++ks) {
+            const int subl = ks / pb.ksub[q];
+            const int k0 = (ks - subl * pb.ksub[q]) * BK;
+            const int sub = subl + b * pb.sub_per_batch[q];
             const int ab = b * pb.a_bmul[q] + sub * pb.a_smul[q];
             const int bb = b * pb.b_bmul[q] + sub * pb.b_smul[q];
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -142,12 +156,14 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
+        const int b = tile / tiles_per_batch;
         ptx::mbar_wait(&tempty_bar[buf], bphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         uint32_t accum = 0;
         for (int q = 0; q < pb.num_pairs; ++q) {
-          for (int ks = 0; ks < pb.ksteps[q]; ++ks) {
+          const int nks = ksteps_of(pb, q, b);
+          for (int ks = 0; ks < nks; ++ks) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -170,6 +186,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
     const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - kEpiWarp0) >> 2;      // 0/1: which alternate chunks this warp takes
     Epi epi(ep);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -184,7 +201,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       const int m = m0 + q4 * 32 + lane;
       epi.tile_begin(b, m, n0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * BN + c * 32, v);
         ptx::tmem_ld_wait();
@@ -193,7 +210,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
-      epi.tile_end(b, m, n0, rem % pb.tiles_n);
+      epi.tile_end(b, m, n0, rem % pb.tiles_n, half);
     }
   }
 

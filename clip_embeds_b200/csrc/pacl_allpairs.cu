@@ -24,6 +24,7 @@
 namespace clipk {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kDthSplits = 6;   // split-K slabs of the text-gradient accumulator
 
 // rn[row] = 1 / max(||x_row||, 1e-12)      (F.normalize denominator, pacl.py:122,125)
 __global__ void rownorm_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t rows, int D, float* __restrict__ rn) {
@@ -68,13 +69,18 @@ __global__ void allpairs_alpha_beta_kernel(const float* __restrict__ num, const 
 
 // dT_k = rnT_k (dth_k - t^_k <t^_k, dth_k>),  t^ = T rnT      (Jacobian of F.normalize on the text side)
 __global__ void dtext_finalize_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT,
-                                      const float* __restrict__ dth, int Bt, int D, float* __restrict__ dT) {
+                                      float* __restrict__ dth, int nslab, int Bt, int D, float* __restrict__ dT) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= Bt) return;
   const int lane = threadIdx.x & 31;
   const float rt = rnT[row];
   float dot = 0.f;
-  for (int d = lane; d < D; d += 32) dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, dth[(int64_t)row * D + d], dot);
+  for (int d = lane; d < D; d += 32) {
+    float g = 0.f;
+    for (int s2 = 0; s2 < nslab; ++s2) g += dth[((int64_t)s2 * Bt + row) * D + d];
+    dth[(int64_t)row * D + d] = g;   // slab 0 now holds the total (each thread touches only its own d)
+    dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, g, dot);
+  }
   dot = ptx::warp_sum(dot);
   for (int d = lane; d < D; d += 32) {
     const float th = __bfloat162float(T[(int64_t)row * D + d]) * rt;
@@ -106,7 +112,7 @@ static size_t ap_carve(ApWorkspace* w, void* base, int Bi, int Bt, int P, int D,
     w->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
     w->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
     w->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
-    w->dth = static_cast<float*>(take((size_t)Bt * D * 4));
+    w->dth = static_cast<float*>(take((size_t)kDthSplits * Bt * D * 4));
   }
   return off;
 }
@@ -130,12 +136,21 @@ static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, in
   a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
   b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
   const int ks[1] = {(D + 63) / 64};
-  epi::PaclAct::Params ep{rnV0, rnT, w.A, with_s ? w.S : nullptr, num0, Bt, P, Ppad, act};
+  if (with_s) {
+    epi::PaclAct<true>::Params ep{rnV0, rnT, w.A, w.S, num0, Bt, P, Ppad, act};
+    switch (pick_bn(Ppad)) {
+      case 256: return launch_gemm<256, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+      case 192: return launch_gemm<192, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+      case 128: return launch_gemm<128, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+      default: return launch_gemm<64, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    }
+  }
+  epi::PaclAct<false>::Params ep{rnV0, rnT, w.A, nullptr, num0, Bt, P, Ppad, act};
   switch (pick_bn(Ppad)) {
-    case 256: return launch_gemm<256, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 192: return launch_gemm<192, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 128: return launch_gemm<128, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    default: return launch_gemm<64, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 256: return launch_gemm<256, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 192: return launch_gemm<192, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 128: return launch_gemm<128, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    default: return launch_gemm<64, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
   }
 }
 
@@ -205,7 +220,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   const int Ppad = round_up(P, 64);
   const int64_t n = (int64_t)Bi * Bt;
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dsdot, 0, (size_t)Bi * P * 4, st));
-  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)Bt * D * 4, st));
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
   allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, w.alpha, w.beta);
   for (int i0 = 0; i0 < Bi; i0 += group) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
@@ -240,15 +255,21 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       }
       CLIPK_TRY(r);
     }
-    // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch)
+    // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch; split-K over images so that
+    //     nsplit x tiles CTAs are busy; each split accumulates into its own fp32 slab, summed in the finalize)
     {
+      const int want = gi < kDthSplits ? gi : kDthSplits;
+      const int spb = (gi + want - 1) / want;                // images per split (last split may be shorter)
+      const int nsplit = (gi + spb - 1) / spb;               // no empty split: an empty K range leaves TMEM undefined
       OperandDesc a, b;
       a.ptr = w.E; a.rows = Bt; a.k = Ppad; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
+      a.sub_per_batch = spb;
+      a.sub_total = gi;
       b.ptr = V0; b.mn_major = true; b.rows = D; b.k = P; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 0; b.smul = 1;
-      const int ks[1] = {gi * (Ppad / 64)};
+      const int ks[1] = {spb * (Ppad / 64)};
       const int ksub[1] = {Ppad / 64};
-      epi::Store<false>::Params ep{w.dth, D, 0, Bt, D, 1.f, 1};
-      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, 1, ep, st));
+      epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
+      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, nsplit, ep, st));
     }
     // K6: dV_i = A_i^T G_i + DS'_i^T T - rnV^2 dsdot V
     {
@@ -264,7 +285,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, st));
     }
   }
-  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, Bt, D, dT);
+  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, kDthSplits, Bt, D, dT);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

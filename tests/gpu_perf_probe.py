@@ -63,11 +63,39 @@ def allpairs(B, P, D, group=None):
           f"-> {B / tb * 1e3:.0f} pairs/s, {fl / tb / 1e9:.0f} TFLOP/s algorithmic", flush=True)
 
 
+def allpairs_once(B, P, D, group):
+    V = torch.randn(B, P, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    T = torch.randn(B, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    g = torch.randn(B, B, device="cuda") / B
+    s = Fk.pacl_scores(V, T, 10.0, "sigmoid", group)
+    s.backward(g)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
-    gemm(4096, 4096, 4096)
-    gemm(8192, 8192, 768)
-    gemm(1024, 576, 768, nb=16)
-    gemm(1024, 768, 576, nb=16, b_mn=1)
-    gemm(576, 768, 1024, nb=16, a_mn=1, b_mn=1)
-    for grp in (4, 8, 16):
-        allpairs(1024, 576, 768, grp)
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if cmd in ("gemm", "all"):
+        gemm(4096, 4096, 4096)
+        for nb in (16, 64, 256):
+            gemm(1024, 576, 768, nb=nb)
+        gemm(1024, 768, 576, nb=64, b_mn=1)
+        gemm(576, 768, 1024, nb=64, a_mn=1, b_mn=1)
+    if cmd in ("ap", "all"):
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+        groups = [int(x) for x in sys.argv[3:]] or [16, 32, 64]
+        for grp in groups:
+            allpairs(B, 576, 768, grp)
+    if cmd == "once":
+        allpairs_once(int(sys.argv[2]), 576, 768, int(sys.argv[3]))
+    if cmd == "tile":
+        gemm(1024, 576, 768, nb=64)
+        gemm(1024, 576, 6144, nb=8)
+        gemm(1024, 512, 768, nb=64)
+        gemm(1024, 1024, 768, nb=32)
+        gemm(2048, 2048, 768, nb=4)
+    if cmd == "fwdonce":
+        V = torch.randn(int(sys.argv[2]), 576, 768, device="cuda").to(torch.bfloat16)
+        T = torch.randn(1024, 768, device="cuda").to(torch.bfloat16)
+        with torch.no_grad():
+            Fk.pacl_scores(V, T, 10.0, "sigmoid", int(sys.argv[3]))
+        torch.cuda.synchronize()
