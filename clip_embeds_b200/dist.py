@@ -115,3 +115,27 @@ class _AllGatherGradCPU(torch.autograd.Function):
 def _splice_local(all_x, local_x, rank_):
     n = local_x.shape[0]
     return torch.cat([all_x[: rank_ * n], local_x, all_x[(rank_ + 1) * n:]], dim=0)
+
+
+def all_reduce_sum_(x, group=None):
+    dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+    return x
+
+
+class _AllReduceSumGrad(torch.autograd.Function):
+    """y = sum over ranks of x (for logging the global loss); backward is the identity on the local x, which is
+    the correct gradient of the GLOBAL loss w.r.t. this rank's contribution."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.detach().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def all_reduce_sum_with_grad(x, group=None):
+    return _AllReduceSumGrad.apply(x, group)

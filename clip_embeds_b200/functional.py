@@ -304,3 +304,146 @@ def feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0):
     ignore_index = any negative label).  labels=None means label_i = i + label_offset."""
     loss_sum, valid = _FeatRowCE.apply(X, Y, scale, bias, labels, int(label_offset))
     return loss_sum / valid.sum().clamp_min(1)
+
+
+# --------------------------------------------------------------------------------------------- SPARC
+class _SparcAlign(torch.autograd.Function):
+    """sparc.forward alignment (pacl.py:453-478): (V raw [B,P,D], L raw [B,T,D]) -> (n(L), n(G)) fp32."""
+
+    @staticmethod
+    def forward(ctx, V, L, sigma):
+        _need_cuda(V, L)
+        Vb = V.to(torch.bfloat16).contiguous()
+        Lb = L.to(torch.bfloat16).contiguous()
+        B, P, D = Vb.shape
+        T = Lb.shape[1]
+        dev = Vb.device
+        l_hat, g_hat = _f32(B, T, D, device=dev), _f32(B, T, D, device=dev)
+        lnorm, gnorm = _f32(B, T, device=dev), _f32(B, T, device=dev)
+        nbytes = _lib.lib().clipk_sparc_workspace_bytes(B, T, P, D, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_sparc_align_fwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, float(sigma), l_hat.data_ptr(),
+                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        ctx.save_for_backward(Vb, Lb, l_hat, g_hat, lnorm, gnorm)
+        ctx.cfg = (float(sigma), V.dtype, L.dtype)
+        return l_hat, g_hat
+
+    @staticmethod
+    def backward(ctx, d_l_hat, d_g_hat):
+        Vb, Lb, l_hat, g_hat, lnorm, gnorm = ctx.saved_tensors
+        sigma, v_dtype, l_dtype = ctx.cfg
+        B, P, D = Vb.shape
+        T = Lb.shape[1]
+        dev = Vb.device
+        d_l_hat = (torch.zeros_like(l_hat) if d_l_hat is None else d_l_hat.float()).contiguous()
+        d_g_hat = (torch.zeros_like(g_hat) if d_g_hat is None else d_g_hat.float()).contiguous()
+        out_bf16 = v_dtype == torch.bfloat16
+        dV = torch.empty(B, P, D, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        dL = _f32(B, T, D, device=dev)
+        nbytes = _lib.lib().clipk_sparc_workspace_bytes(B, T, P, D, 1)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_sparc_align_bwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, sigma, l_hat.data_ptr(),
+                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), d_g_hat.data_ptr(), d_l_hat.data_ptr(), 0,
+                  dV.data_ptr(), 1 if out_bf16 else 0, dL.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        return dV.to(v_dtype), dL.to(l_dtype), None
+
+
+def sparc_align(v_patch_embed, l_token_embed, sigma):
+    """Returns (l_token_embed_normalised, l_grouped_v_patch_embed_normalised), both fp32 [B,T,D]."""
+    return _SparcAlign.apply(v_patch_embed, l_token_embed, sigma)
+
+
+class _MeanDim1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X):
+        _need_cuda(X)
+        if X.dtype not in _DT:
+            X = X.float()
+        Xc = X.contiguous()
+        B, R, D = Xc.shape
+        out = _f32(B, D, device=Xc.device)
+        _lib.call("clipk_mean_dim1", Xc.data_ptr(), _DT[Xc.dtype], B, R, D, out.data_ptr(), _stream())
+        ctx.cfg = (R, X.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        R, dt = ctx.cfg
+        return (g / R).to(dt).unsqueeze(1).expand(-1, R, -1)
+
+
+def mean_dim1(X):
+    return _MeanDim1.apply(X)
+
+
+class _NormalizeRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X):
+        _need_cuda(X)
+        Xc = X.float().contiguous()
+        D = Xc.shape[-1]
+        rows = Xc.numel() // D
+        out = torch.empty_like(Xc)
+        norm = _f32(rows, device=Xc.device)
+        _lib.call("clipk_normalize_rows_fwd", Xc.data_ptr(), rows, D, out.data_ptr(), norm.data_ptr(), _stream())
+        ctx.save_for_backward(out, norm)
+        ctx.dt = X.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, norm = ctx.saved_tensors
+        D = out.shape[-1]
+        g = g.float().contiguous()
+        dx = torch.empty_like(out)
+        _lib.call("clipk_normalize_rows_bwd", out.data_ptr(), g.data_ptr(), norm.data_ptr(), out.numel() // D, D,
+                  dx.data_ptr(), _stream())
+        return dx.to(ctx.dt)
+
+
+def normalize_rows(X):
+    """F.normalize(X, dim=-1) in fp32."""
+    return _NormalizeRows.apply(X)
+
+
+class _SparcLocal(torch.autograd.Function):
+    """1/2 [ masked_pairwise(g_hat, l_hat) + masked_pairwise(l_hat, g_hat) ]  (pacl.py:522-556, :575-582).
+    `mask_sum` may be a GLOBAL mask count (image-sharded training): the returned value is then this rank's
+    contribution sum_b(...) / (2 * mask_sum)."""
+
+    @staticmethod
+    def forward(ctx, g_hat, l_hat, mask, scale, mask_sum):
+        _need_cuda(g_hat, l_hat, mask)
+        a = g_hat.float().contiguous()
+        b = l_hat.float().contiguous()
+        m = mask.float().contiguous()
+        B, T, D = a.shape
+        dev = a.device
+        loss_sum = _f32(B, device=dev)
+        nbytes = _lib.lib().clipk_sparc_local_workspace_bytes(B, T, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_sparc_local_fwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), B, T, D, float(scale),
+                  loss_sum.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        msum = m.sum() if mask_sum is None else mask_sum.float()
+        ctx.save_for_backward(a, b, m, msum)
+        ctx.cfg = (float(scale), g_hat.dtype, l_hat.dtype)
+        return loss_sum.sum() * 0.5 / msum
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, m, msum = ctx.saved_tensors
+        scale, adt, bdt = ctx.cfg
+        B, T, D = a.shape
+        dev = a.device
+        wgt = (g.float() * 0.5 / msum).reshape(1).contiguous()
+        d_a, d_b = torch.empty_like(a), torch.empty_like(b)
+        scratch = _f32(B, device=dev)
+        nbytes = _lib.lib().clipk_sparc_local_workspace_bytes(B, T, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_sparc_local_bwd", a.data_ptr(), b.data_ptr(), m.data_ptr(), B, T, D, scale, wgt.data_ptr(),
+                  d_a.data_ptr(), d_b.data_ptr(), scratch.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        return d_a.to(adt), d_b.to(bdt), None, None, None
+
+
+def sparc_local_loss(g_hat, l_hat, mask, scale, mask_sum=None):
+    return _SparcLocal.apply(g_hat, l_hat, mask, scale, mask_sum)

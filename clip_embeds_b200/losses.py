@@ -103,3 +103,44 @@ class OpenClipLoss(nn.Module):
             lt = Fk.feat_row_ce(text_features, image_features, logit_scale, bias, lab_t, 0)
         total = (li + lt) / 2
         return {"contrastive_loss": total} if output_dict else total
+
+
+class SparcLoss(ClipLoss):
+    """SparcLoss (pacl.py:516-584): 0.5 * global InfoNCE on mean-pooled features + 1.0 * masked per-sample
+    token <-> grouped-patch contrastive loss (both directions).
+
+    With `group` set (one process per GPU, samples sharded), the global term gathers the two [b,D] pooled
+    features (gradient: reduce-scatter) and the local term divides by the GLOBAL mask count, as the reference's
+    DataParallel run does (outputs gathered before the loss, train_sparc.py:92-94); the returned value is the
+    global loss, identical on every rank."""
+
+    def __init__(self, temperature, group=None):
+        super().__init__(temperature)
+        self.global_weight = 0.5
+        self.local_weight = 1.0
+        self.group = group
+
+    def forward(self, v_patch_embed, l_token_embed, l_grouped_v_patch_embed, language_mask):
+        gi = Fk.normalize_rows(Fk.mean_dim1(v_patch_embed))
+        gt = Fk.normalize_rows(Fk.mean_dim1(l_token_embed))
+        pg = self.group
+        W = cdist.world_size(pg) if pg is not None else 1
+        if W > 1:
+            b = gi.shape[0]
+            all_i = cdist.all_gather_with_grad(gi, pg)
+            all_t = cdist.all_gather_with_grad(gt, pg)
+            off = cdist.rank(pg) * b
+            # rows of this rank against everything; every rank contributes its rows' sum, mean over the global N
+            li = Fk.feat_row_ce(gi, all_t, self.logit_scale, 0.0, None, off) * (b / all_i.shape[0])
+            lt = Fk.feat_row_ce(gt, all_i, self.logit_scale, 0.0, None, off) * (b / all_i.shape[0])
+            global_part = (li + lt) / 2
+            msum = language_mask.float().sum()
+            cdist.all_reduce_sum_(msum, pg)
+            local_part = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale, msum)
+            total = self.global_weight * global_part + self.local_weight * local_part
+            return cdist.all_reduce_sum_with_grad(total, pg)
+        li = Fk.feat_row_ce(gi, gt, self.logit_scale)
+        lt = Fk.feat_row_ce(gt, gi, self.logit_scale)
+        global_loss = (li + lt) / 2
+        local_loss = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale)
+        return self.global_weight * global_loss + self.local_weight * local_loss

@@ -121,6 +121,38 @@ int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float s
                       const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * SPARC token-to-patch alignment (sparc.forward, PACL/model/pacl.py:453-478):
+ *   S = L V^T (raw), min-max over patches, threshold sigma, row-normalise, G = W V; outputs l_hat = n(L),
+ *   g_hat = n(G) (fp32 [B,T,D]) and their norms [B,T] (saved for backward).  V bf16 [B,P,D], L bf16 [B,T,D], T <= 128.
+ * Backward recomputes S / W inside `workspace`; d_g_hat, d_l_hat fp32 [B,T,D]; g_add (nullable) fp32 [B,D] is added
+ * to every patch row of dV (the broadcast gradient of mean_p V from SparcLoss's global term, pacl.py:561);
+ * dV [B,P,D] bf16 (dv_bf16 != 0) or fp32; dL fp32 [B,T,D].
+ */
+size_t clipk_sparc_workspace_bytes(int B, int T, int P, int D, int backward);
+int clipk_sparc_align_fwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, float* l_hat,
+                          float* g_hat, float* lnorm, float* gnorm, void* workspace, size_t ws_bytes, void* stream);
+int clipk_sparc_align_bwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, const float* l_hat,
+                          const float* g_hat, const float* lnorm, const float* gnorm, const float* d_g_hat,
+                          const float* d_l_hat, const float* g_add, void* dV, int dv_bf16, float* dL, void* workspace,
+                          size_t ws_bytes, void* stream);
+
+/* SparcLoss local term, both directions (masked_pairwise_contrastive_loss, pacl.py:522-556; a = g_hat, b = l_hat
+ * fp32 [B,T,D], mask fp32 [B,T]).  fwd: loss_sum [B]; total local loss = sum_b loss_sum / (2 * sum(mask)).
+ * bwd: wgt = DEVICE scalar (upstream * 0.5 / sum(mask)); d_a, d_b fp32 [B,T,D]; loss_sum_scratch [B]. */
+size_t clipk_sparc_local_workspace_bytes(int B, int T, int D);
+int clipk_sparc_local_fwd(const float* a, const float* b, const float* mask, int B, int T, int D, float scale,
+                          float* loss_sum, void* workspace, size_t ws_bytes, void* stream);
+int clipk_sparc_local_bwd(const float* a, const float* b, const float* mask, int B, int T, int D, float scale,
+                          const float* wgt, float* d_a, float* d_b, float* loss_sum_scratch, void* workspace,
+                          size_t ws_bytes, void* stream);
+
+/* torch.mean(X, dim=1) for X [B,R,D] (bf16 | fp32) -> fp32 [B,D] (pacl.py:443-447, :561-562) and F.normalize rows. */
+int clipk_mean_dim1(const void* X, int dtype, int B, int R, int D, float* out, void* stream);
+int clipk_normalize_rows_fwd(const float* X, int64_t rows, int D, float* out, float* norm, void* stream);
+int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm, int64_t rows, int D, float* dx,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
