@@ -14,6 +14,7 @@ c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, 
 SIGNATURES = {
     "clipk_last_error": (ctypes.c_char_p, []),
     "clipk_version": (c_int, []),
+    "clipk_launch_count": (ctypes.c_ulonglong, []),
     "clipk_check_device": (c_int, []),
     "clipk_gemm_bf16": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_i64, c_int,
                                 c_int, c_int, c_int, c_int, c_f32, c_int, c_vp]),

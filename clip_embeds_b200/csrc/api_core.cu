@@ -9,6 +9,8 @@
 namespace clipk {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -115,5 +117,6 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
 extern "C" {
 const char* clipk_last_error(void) { return clipk::g_err; }
 int clipk_version(void) { return 100; }
+unsigned long long clipk_launch_count(void) { return clipk::g_launches.load(std::memory_order_relaxed); }
 int clipk_check_device(void) { return clipk::check_device(); }
 }

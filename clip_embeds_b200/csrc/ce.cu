@@ -302,6 +302,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
   CLIPK_TRY(launch_gemm<256, false, false, epi::LsePart>(&a, &b, 1, ks, ks, M, N, 1, ep, st));
   lse_merge_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -359,6 +360,7 @@ int clipk_ce_rows(const float* L, int M, int N, int64_t ld, const int64_t* label
   if (M == 0) return 0;
   clipk::ce_rows_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, labels, label_offset,
                                                                                     row_lse, row_loss);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -367,6 +369,7 @@ int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, floa
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_cols: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
   clipk::ce_cols_kernel<<<(N + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, col_max, col_sum);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -379,6 +382,7 @@ int clipk_ce_scores_grad(const float* L, int M, int N, int64_t ld, const float* 
   const int64_t n = (int64_t)M * N;
   clipk::ce_scores_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       L, M, N, ld, row_lse, col_lse, label_offset, w_row, w_col, dL);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -391,6 +395,7 @@ int clipk_ce_rows_grad(const float* L, int M, int N, int64_t ld, const float* ro
   const int64_t n = (int64_t)M * N;
   clipk::ce_rows_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       L, M, N, ld, row_lse, labels, label_offset, row_w, dL);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -403,6 +408,7 @@ int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   clipk::sgemm_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc, M,
                                                                                    N, K, alpha, beta);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,6 +17,7 @@ namespace clipk {
 void set_error(const char* fmt, ...);          // thread-local message returned by clipk_last_error()
 int check_device();                            // 0 if the current device is sm_100 (B200), else CLIPK_ERR_ARCH
 int sm_count();                                // SM count of the current device
+void count_launches(int n);                    // bump the library-wide kernel-launch counter (clipk_launch_count)
 
 #define CLIPK_CHECK_CUDA(expr)                                                                       \
   do {                                                                                               \
@@ -105,6 +106,7 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
   }
   const int grid = total < sm_count() ? total : sm_count();
   kern<<<grid, eng::kThreads, L::kTotal, stream>>>(maps, pb, ep);
+  count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

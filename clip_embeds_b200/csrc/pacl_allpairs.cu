@@ -191,7 +191,9 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
   rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
+  clipk::count_launches(1);
   rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
   for (int i0 = 0; i0 < Bi; i0 += group) {
@@ -206,6 +208,7 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   }
   const int64_t n = (int64_t)Bi * Bt;
   allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -222,6 +225,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dsdot, 0, (size_t)Bi * P * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
   allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, w.alpha, w.beta);
+  clipk::count_launches(1);
   for (int i0 = 0; i0 < Bi; i0 += group) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
     const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
@@ -286,6 +290,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     }
   }
   dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, kDthSplits, Bt, D, dT);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

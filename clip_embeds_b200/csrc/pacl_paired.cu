@@ -243,6 +243,7 @@ static int paired_fwd_t(const void* V, const void* Tx, int B, int v_div, int P, 
     auto k = pacl_paired_fwd_kernel<T, N>;                                                                     \
     CLIPK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     k<<<B, kPairedThreads, smem, st>>>((const T*)V, (const T*)Tx, B, v_div, P, D, act, act_out, img, txt, cosine, stats); \
+    clipk::count_launches(1); \
   }
   switch (nit) {
     case 1: LAUNCH(1) break;
@@ -267,6 +268,7 @@ static int paired_bwd_t(const void* V, const void* Tx, int B, int P, int D, int 
     auto k = pacl_paired_bwd_kernel<T, N>;                                                                     \
     CLIPK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     k<<<B, kPairedThreads, smem, st>>>((const T*)V, (const T*)Tx, B, P, D, act, img, stats, d_img, d_txt, (T*)dV, (T*)dT); \
+    clipk::count_launches(1); \
   }
   switch (nit) {
     case 1: LAUNCH(1) break;

@@ -316,6 +316,7 @@ static int sparc_scores_and_weights(const __nv_bfloat16* V, const __nv_bfloat16*
   CLIPK_TRY(launch_bn<epi::Store<false>, false, false>(bn, &a, &b, 1, ks, T, P, B, ep, st));
   const int64_t rows = (int64_t)B * T;
   sparc_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, rows, P, Ppad, sigma, w.W, w.stats, w.arg);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -341,7 +342,9 @@ int sparc_align_fwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T
   }
   const int64_t rows = (int64_t)B * T;
   normalize_rows_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.Graw, rows, D, g_hat, nullptr, gnorm);
+  clipk::count_launches(1);
   normalize_rows_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(L, rows, D, l_hat, nullptr, lnorm);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -361,7 +364,9 @@ int sparc_align_bwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T
   CLIPK_TRY(sparc_scores_and_weights(V, L, B, T, P, D, sigma, w, st));       // recompute S, W, stats
   // dG (raw) = Jacobian of n(G) ; dL_direct = Jacobian of n(L)
   normalize_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g_hat, d_g_hat, gnorm, rows, D, nullptr, 0, w.dG);
+  clipk::count_launches(1);
   normalize_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(l_hat, d_l_hat, lnorm, rows, D, dL, 0, nullptr);
+  clipk::count_launches(1);
   // dW = dG V^T
   {
     OperandDesc a, b;
@@ -373,6 +378,7 @@ int sparc_align_bwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T
     CLIPK_TRY(launch_bn<epi::Store<false>, false, false>(bn, &a, &b, 1, ks, T, P, B, ep, st));
   }
   sparc_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, w.dW, rows, P, Ppad, sigma, w.stats, w.arg, w.dS);
+  clipk::count_launches(1);
   // dL += dS V
   {
     OperandDesc a, b;
@@ -431,8 +437,13 @@ int clipk_mean_dim1(const void* X, int dtype, int B, int R, int D, float* out, v
   if (B == 0) return 0;
   dim3 grid((D + 255) / 256, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == CLIPK_BF16) clipk::mean_dim1_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), R, D, out);
-  else if (dtype == CLIPK_F32) clipk::mean_dim1_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(X), R, D, out);
+  if (dtype == CLIPK_BF16) {
+    clipk::mean_dim1_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), R, D, out);
+    clipk::count_launches(1);
+  } else if (dtype == CLIPK_F32) {
+    clipk::mean_dim1_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(X), R, D, out);
+    clipk::count_launches(1);
+  }
   else { clipk::set_error("mean_dim1: bad dtype %d", dtype); return CLIPK_ERR_INVALID; }
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -444,6 +455,7 @@ int clipk_normalize_rows_fwd(const float* X, int64_t rows, int D, float* out, fl
   if (rows == 0) return 0;
   clipk::normalize_rows_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       X, rows, D, out, nullptr, norm);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -453,6 +465,7 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
   if (rows == 0) return 0;
   clipk::normalize_rows_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       xh, g, norm, rows, D, dx, 0, nullptr);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -498,7 +511,9 @@ static int sparc_local_logits(const float* a, const float* b, int B, int T, int 
   const int Tp = rup(T, 8);
   const int64_t n = (int64_t)B * T * D;
   cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, w.a16);
+  clipk::count_launches(1);
   cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b, n, w.b16);
+  clipk::count_launches(1);
   OperandDesc oa, ob;
   oa.ptr = w.a16; oa.rows = T; oa.k = D; oa.ld = D; oa.batch = B; oa.batch_stride = (int64_t)T * D; oa.bmul = 1;
   ob.ptr = w.b16; ob.rows = T; ob.k = D; ob.ld = D; ob.batch = B; ob.batch_stride = (int64_t)T * D; ob.bmul = 1;
@@ -525,6 +540,7 @@ int clipk_sparc_local_fwd(const float* a, const float* b, const float* mask, int
   const size_t smem = (size_t)(T * (T + 1) + 3 * T) * sizeof(float);
   CLIPK_CHECK_CUDA(cudaFuncSetAttribute(clipk::sparc_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   clipk::sparc_local_kernel<<<B, 256, smem, st>>>(w.Z, T, Tp, mask, loss_sum, nullptr, nullptr, Tp);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -545,6 +561,7 @@ int clipk_sparc_local_bwd(const float* a, const float* b, const float* mask, int
   const size_t smem = (size_t)(T * (T + 1) + 3 * T) * sizeof(float);
   CLIPK_CHECK_CUDA(cudaFuncSetAttribute(sparc_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sparc_local_kernel<<<B, 256, smem, st>>>(w.Z, T, Tp, mask, loss_sum_scratch, wgt, w.dZ, Tp);
+  clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   const int ks[1] = {(T + 63) / 64};
   {  // d_a = scale * dZ b

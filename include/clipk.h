@@ -37,6 +37,8 @@ extern "C" {
 
 const char* clipk_last_error(void);
 int clipk_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta) */
+unsigned long long clipk_launch_count(void);
 /* 0 when the current CUDA device can run the kernels (compute capability 10.x), else CLIPK_ERR_ARCH. */
 int clipk_check_device(void);
 
