@@ -181,6 +181,30 @@ def _merge_cols(col_max, col_sum, group=None):
     return col_max + torch.log(col_sum)
 
 
+def _k_ce_rows(L, offset):
+    """row_lse [M], row_loss [M] of a fp32 matrix (label of row i = i + offset)."""
+    M, N = L.shape
+    row_lse, row_loss = _f32(M, device=L.device), _f32(M, device=L.device)
+    _lib.call("clipk_ce_rows", L.data_ptr(), M, N, N, 0, offset, row_lse.data_ptr(), row_loss.data_ptr(), _stream())
+    return row_lse, row_loss
+
+
+def _k_ce_cols(L):
+    """per-column (max, sum exp(L - max)) over the local rows."""
+    M, N = L.shape
+    col_max, col_sum = _f32(N, device=L.device), _f32(N, device=L.device)
+    _lib.call("clipk_ce_cols", L.data_ptr(), M, N, N, col_max.data_ptr(), col_sum.data_ptr(), _stream())
+    return col_max, col_sum
+
+
+def _k_ce_scores_grad(L, row_lse, col_lse, offset, w_row, w_col):
+    M, N = L.shape
+    dL = torch.empty_like(L)
+    _lib.call("clipk_ce_scores_grad", L.data_ptr(), M, N, N, row_lse.data_ptr(), col_lse.data_ptr(), offset, w_row,
+              w_col, dL.data_ptr(), _stream())
+    return dL
+
+
 class _ScoreInfoNCE(torch.autograd.Function):
     """loss = 1/2 [ CE(L, arange) + CE(L^T, arange) ] for a score matrix L (pacl.py:509-512 applied to scores).
 
@@ -189,15 +213,10 @@ class _ScoreInfoNCE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, L, offset, group):
-        _need_cuda(L)
         L = L.float().contiguous()
         M, N = L.shape
-        dev = L.device
-        row_lse, row_loss = _f32(M, device=dev), _f32(M, device=dev)
-        col_max, col_sum = _f32(N, device=dev), _f32(N, device=dev)
-        st = _stream()
-        _lib.call("clipk_ce_rows", L.data_ptr(), M, N, N, 0, offset, row_lse.data_ptr(), row_loss.data_ptr(), st)
-        _lib.call("clipk_ce_cols", L.data_ptr(), M, N, N, col_max.data_ptr(), col_sum.data_ptr(), st)
+        row_lse, row_loss = _k_ce_rows(L, offset)
+        col_max, col_sum = _k_ce_cols(L)
         col_lse = _merge_cols(col_max, col_sum, group)
         diag = row_lse - row_loss                                        # L[i, i + offset]
         part = torch.stack([row_loss.sum(), (col_lse[offset:offset + M] - diag).sum()])
@@ -205,9 +224,7 @@ class _ScoreInfoNCE(torch.autograd.Function):
             import torch.distributed as dist
             dist.all_reduce(part, group=group)
         loss = 0.5 * (part[0] + part[1]) / N
-        dL = torch.empty_like(L)
-        _lib.call("clipk_ce_scores_grad", L.data_ptr(), M, N, N, row_lse.data_ptr(), col_lse.data_ptr(), offset,
-                  0.5 / N, 0.5 / N, dL.data_ptr(), st)
+        dL = _k_ce_scores_grad(L, row_lse, col_lse.contiguous(), offset, 0.5 / N, 0.5 / N)
         ctx.save_for_backward(dL)
         return loss
 

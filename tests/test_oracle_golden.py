@@ -1,0 +1,90 @@
+"""CPU: the oracle restatement (oracle/ref_oracle.py) must reproduce the committed outputs of the real reference
+(tests/golden/goldens.pt, produced by oracle/make_golden.py from /root/reference)."""
+import torch
+
+from conftest import rel_l2
+from oracle import ref_oracle as O
+
+
+def test_g1_paired(goldens):
+    for key, act in (("G1", "sigmoid"), ("G1b", "ones")):
+        G = goldens[key]
+        V = O.rn(1, 4, 196, 512).requires_grad_()
+        T = O.rn(2, 4, 512).requires_grad_()
+        img, txt = O.pacl_forward(V, T, act)
+        loss = O.pacl_clip_loss(img, txt, 0.1)
+        loss.backward()
+        assert torch.allclose(O.patch_alignment(V, T).detach(), G["a"], atol=1e-6)
+        assert torch.allclose(img.detach(), G["img"], atol=1e-6)
+        assert abs(loss.item() - G["loss"].item()) < 2e-6
+        assert rel_l2(V.grad, G["dV"]) < 1e-5 and rel_l2(T.grad, G["dT"]) < 1e-5
+
+
+def test_g1_values_match_survey(goldens):
+    # SURVEY.md Appendix B pins (survey-time run of the reference)
+    assert abs(goldens["G1"]["loss"].item() - 0.5694192051887512) < 1e-6
+    assert abs(goldens["G1b"]["loss"].item() - 1.2633897066116333) < 1e-6
+    assert abs(goldens["G2"]["loss"].item() - 2.728726863861084) < 2e-6
+    assert abs(goldens["G3"]["loss"].item() - 44.59129333496094) < 1e-4
+    assert goldens["G4"]["top1"].tolist() == [3, 0, 3, 0, 0, 0, 1, 0, 3, 3, 2, 1, 1, 0, 2, 1]
+    assert torch.allclose(goldens["G5"]["local"]["loss"], torch.tensor([6.744038, 9.403412]), atol=1e-5)
+    assert torch.allclose(goldens["G5"]["global"]["loss"], torch.tensor([8.073725, 8.073725]), atol=1e-5)
+
+
+def test_g2_sparc(goldens):
+    G = goldens["G2"]
+    B, T_, P, D = 4, 77, 196, 512
+    V = O.rn(3, B, P, D).requires_grad_()
+    L = O.rn(4, B, T_, D).requires_grad_()
+    mask = (torch.arange(T_).expand(B, -1) <= G["eot"].unsqueeze(1)).float()
+    v, lh, gh, _ = O.sparc_forward(V, L, mask, 1.0 / P)
+    loss = O.sparc_loss(v, lh, gh, mask, 0.1)
+    loss.backward()
+    assert torch.allclose(gh.detach(), G["g_hat"], atol=1e-6)
+    assert abs(loss.item() - G["loss"].item()) < 5e-6
+    assert rel_l2(V.grad, G["dV"]) < 1e-4 and rel_l2(L.grad, G["dL"]) < 1e-4
+
+
+def test_g3_openclip(goldens):
+    G = goldens["G3"]
+    img = O.l2n(O.rn(5, 8, 16)).requires_grad_()
+    txt = O.l2n(O.rn(6, 11, 16)).requires_grad_()
+    loss = O.openclip_loss_single(img, txt, 100.0, usehardtext=True)
+    loss.backward()
+    assert abs(loss.item() - G["loss"].item()) < 1e-4
+    assert rel_l2(img.grad, G["dimg"]) < 1e-5 and rel_l2(txt.grad, G["dtxt"]) < 1e-5
+
+
+def test_g4_eval_top1(goldens):
+    V = O.rn(7, 16, 576, 768)
+    T = O.rn(8, 16, 4, 768)
+    top1, scores = O.eval_top1(V, T, 100.0)
+    assert torch.equal(top1, goldens["G4"]["top1"])
+    assert torch.allclose(scores, goldens["G4"]["scores"], atol=1e-4)
+
+
+def test_g5_multirank_restatement(goldens):
+    g = torch.Generator().manual_seed(0)
+    all_img = O.l2n(torch.randn(8, 8, generator=g))
+    all_txt = O.l2n(torch.randn(8, 8, generator=g))
+    hard0 = O.l2n(torch.randn(1, 8, generator=g))
+    hard1 = O.l2n(torch.randn(3, 8, generator=g))
+    for key, local in (("local", True), ("global", False)):
+        imgs = [all_img[:4].clone().requires_grad_(), all_img[4:].clone().requires_grad_()]
+        txts = [torch.cat([all_txt[:4], hard0]).requires_grad_(), torch.cat([all_txt[4:], hard1]).requires_grad_()]
+        losses = O.openclip_loss_ranks(imgs, txts, 10.0, local_loss=local, usehardtext=True)
+        sum(losses).backward()
+        assert torch.allclose(torch.stack([l.detach() for l in losses]), goldens["G5"][key]["loss"], atol=1e-5)
+        for r in range(2):
+            assert rel_l2(imgs[r].grad, goldens["G5"][key]["dimg"][r]) < 1e-5
+            assert rel_l2(txts[r].grad, goldens["G5"][key]["dtxt"][r]) < 1e-5
+
+
+def test_g6_allpairs(goldens):
+    G = goldens["G6"]
+    V = O.rn(11, 6, 50, 64).requires_grad_()
+    T = O.rn(12, 6, 64).requires_grad_()
+    loss = O.pacl_allpairs_loss(V, T, 0.1)
+    loss.backward()
+    assert abs(loss.item() - G["loss"].item()) < 2e-6
+    assert rel_l2(V.grad, G["dV"]) < 1e-5 and rel_l2(T.grad, G["dT"]) < 1e-5
