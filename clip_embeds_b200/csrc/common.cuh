@@ -60,6 +60,7 @@ struct OperandDesc {
   int smul = 0;
   int sub_per_batch = 0;     // split-K: sub = b * sub_per_batch + (kstep / ksub)
   int sub_total = 0;         // >0: uneven split, batch b covers sub-batches [b*spb, min((b+1)*spb, sub_total))
+  int reverse = 0;           // (read from operand A of pair 0) walk batches downwards
 };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -76,6 +77,7 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
   pb.tiles_m = (M + eng::BM - 1) / eng::BM;
   pb.tiles_n = (N + BN - 1) / BN;
   pb.num_pairs = num_pairs;
+  pb.reverse = a[0].reverse;
   for (int q = 0; q < num_pairs; ++q) {
     pb.ksteps[q] = ksteps[q];
     pb.ksub[q] = ksub[q] > 0 ? ksub[q] : (ksteps[q] > 0 ? ksteps[q] : 1);

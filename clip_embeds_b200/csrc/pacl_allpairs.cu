@@ -68,8 +68,11 @@ __global__ void allpairs_alpha_beta_kernel(const float* __restrict__ num, const 
 }
 
 // dT_k = rnT_k (dth_k - t^_k <t^_k, dth_k>),  t^ = T rnT      (Jacobian of F.normalize on the text side)
+struct DthSlabs {
+  float* p[4];
+};
 __global__ void dtext_finalize_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT,
-                                      float* __restrict__ dth, int nslab, int Bt, int D, float* __restrict__ dT) {
+                                      DthSlabs slabs, int lanes, int nslab, int Bt, int D, float* __restrict__ dT) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= Bt) return;
   const int lane = threadIdx.x & 31;
@@ -77,24 +80,56 @@ __global__ void dtext_finalize_kernel(const __nv_bfloat16* __restrict__ T, const
   float dot = 0.f;
   for (int d = lane; d < D; d += 32) {
     float g = 0.f;
-    for (int s2 = 0; s2 < nslab; ++s2) g += dth[((int64_t)s2 * Bt + row) * D + d];
-    dth[(int64_t)row * D + d] = g;   // slab 0 now holds the total (each thread touches only its own d)
+    for (int l = 0; l < lanes; ++l)
+      for (int s2 = 0; s2 < nslab; ++s2) g += slabs.p[l][((int64_t)s2 * Bt + row) * D + d];
+    slabs.p[0][(int64_t)row * D + d] = g;   // lane 0 / slab 0 now holds the total (each thread touches only its own d)
     dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, g, dot);
   }
   dot = ptx::warp_sum(dot);
   for (int d = lane; d < D; d += 32) {
     const float th = __bfloat162float(T[(int64_t)row * D + d]) * rt;
-    dT[(int64_t)row * D + d] = rt * (dth[(int64_t)row * D + d] - th * dot);
+    dT[(int64_t)row * D + d] = rt * (slabs.p[0][(int64_t)row * D + d] - th * dot);
   }
 }
 
-struct ApWorkspace {
+// Internal stream pool: image groups are issued round-robin on `lanes` side streams (forked from / joined to the
+// caller's stream with events, no host synchronisation) so that the small per-group launches of different groups
+// overlap and fill each other's tails while each group's scratch stays L2-resident.
+constexpr int kMaxLanes = 4;
+struct LanePool {
+  int device = -1;
+  cudaStream_t st[kMaxLanes] = {};
+  cudaEvent_t fork = nullptr, join[kMaxLanes] = {};
+};
+static int get_lanes(LanePool** out) {
+  static thread_local LanePool pools[8];
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  LanePool& p = pools[dev & 7];
+  if (p.device != dev) {
+    for (int i = 0; i < kMaxLanes; ++i) {
+      CLIPK_CHECK_CUDA(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
+      CLIPK_CHECK_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
+    }
+    CLIPK_CHECK_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    p.device = dev;
+  }
+  *out = &p;
+  return 0;
+}
+
+struct ApWorkspace {      // per-lane scratch
   __nv_bfloat16 *A, *G, *DS, *E;
   __half* S;
-  float *dsdot, *alpha, *beta, *dth;
+  float* dth;             // [kDthSplits][Bt][D] fp32 split-K slabs of this lane
 };
 
-static size_t ap_carve(ApWorkspace* w, void* base, int Bi, int Bt, int P, int D, int group, int backward) {
+struct ApShared {
+  float *dsdot, *alpha, *beta, *dth;
+};
+// layout: [lanes x per-lane scratch][shared per-call arrays]
+static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt, int P, int D, int group, int lanes,
+                       int backward) {
   const int Ppad = round_up(P, 64);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -103,16 +138,21 @@ static size_t ap_carve(ApWorkspace* w, void* base, int Bi, int Bt, int P, int D,
     return p;
   };
   const size_t act = (size_t)group * Bt * Ppad * 2;
-  w->A = static_cast<__nv_bfloat16*>(take(act));
+  for (int l = 0; l < lanes; ++l) {
+    w[l].A = static_cast<__nv_bfloat16*>(take(act));
+    if (backward) {
+      w[l].S = static_cast<__half*>(take(act));
+      w[l].DS = static_cast<__nv_bfloat16*>(take(act));
+      w[l].E = static_cast<__nv_bfloat16*>(take(act));
+      w[l].G = static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
+      w[l].dth = static_cast<float*>(take((size_t)kDthSplits * Bt * D * 4));
+    }
+  }
   if (backward) {
-    w->S = static_cast<__half*>(take(act));
-    w->DS = static_cast<__nv_bfloat16*>(take(act));
-    w->E = static_cast<__nv_bfloat16*>(take(act));
-    w->G = static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
-    w->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
-    w->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
-    w->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
-    w->dth = static_cast<float*>(take((size_t)kDthSplits * Bt * D * 4));
+    sh->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
+    sh->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    sh->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    sh->dth = w[0].dth;
   }
   return off;
 }
@@ -159,6 +199,7 @@ static void k2_operands(const ApWorkspace& w, const __nv_bfloat16* V0, int gi, i
                         OperandDesc* b) {
   const int Ppad = round_up(P, 64);
   a->ptr = w.A; a->rows = Bt; a->k = Ppad; a->ld = Ppad; a->batch = gi; a->batch_stride = (int64_t)Bt * Ppad; a->bmul = 1;
+  a->reverse = 1;   // K1 walked the images upwards; start with the activations it wrote last
   b->ptr = V0; b->mn_major = true; b->rows = D; b->k = P; b->ld = D; b->batch = gi; b->batch_stride = (int64_t)P * D; b->bmul = 1;
 }
 
@@ -182,66 +223,101 @@ static int validate(int Bi, int Bt, int P, int D, int act, int group) {
   return 0;
 }
 
+static int fork_lanes(LanePool* lp, int lanes, cudaStream_t st) {
+  CLIPK_CHECK_CUDA(cudaEventRecord(lp->fork, st));
+  for (int l = 0; l < lanes; ++l) CLIPK_CHECK_CUDA(cudaStreamWaitEvent(lp->st[l], lp->fork, 0));
+  return 0;
+}
+static int join_lanes(LanePool* lp, int lanes, cudaStream_t st) {
+  for (int l = 0; l < lanes; ++l) {
+    CLIPK_CHECK_CUDA(cudaEventRecord(lp->join[l], lp->st[l]));
+    CLIPK_CHECK_CUDA(cudaStreamWaitEvent(st, lp->join[l], 0));
+  }
+  return 0;
+}
+
 int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  float* rnV, float* rnT, float* num, float* usq, float* scores, void* ws, size_t ws_bytes, int group,
-                 cudaStream_t st) {
+                 int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
-  ApWorkspace w{};
-  const size_t need = ap_carve(&w, ws, Bi, Bt, P, D, group, 0);
+  CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
+  ApWorkspace w[kMaxLanes]{};
+  ApShared sh{};
+  const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
   rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
-  clipk::count_launches(1);
   rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
-  clipk::count_launches(1);
+  count_launches(2);
   CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
-  for (int i0 = 0; i0 < Bi; i0 += group) {
+  LanePool* lp = nullptr;
+  if (lanes > 1) {
+    CLIPK_TRY(get_lanes(&lp));
+    CLIPK_TRY(fork_lanes(lp, lanes, st));
+  }
+  int gidx = 0;
+  for (int i0 = 0; i0 < Bi; i0 += group, ++gidx) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
+    const int l = gidx % lanes;
+    cudaStream_t ls = lanes > 1 ? lp->st[l] : st;
     const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w, false, num + (int64_t)i0 * Bt, st));
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w[l], false, num + (int64_t)i0 * Bt, ls));
     OperandDesc a, b;
-    k2_operands(w, V0, gi, Bt, P, D, &a, &b);
+    k2_operands(w[l], V0, gi, Bt, P, D, &a, &b);
     const int ks[1] = {Ppad / 64};
     epi::Usq::Params ep{usq + (int64_t)i0 * Bt, Bt, D};
-    CLIPK_TRY(launch_nd<epi::Usq, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, st));
+    CLIPK_TRY(launch_nd<epi::Usq, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
   }
+  if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
   const int64_t n = (int64_t)Bi * Bt;
   allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
-  clipk::count_launches(1);
+  count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  const float* rnV, const float* rnT, const float* num, const float* usq, const float* dscores,
-                 __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, cudaStream_t st) {
+                 __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
-  ApWorkspace w{};
-  const size_t need = ap_carve(&w, ws, Bi, Bt, P, D, group, 1);
+  CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
+  ApWorkspace wl[kMaxLanes]{};
+  ApShared sh{};
+  const size_t need = ap_carve(wl, &sh, ws, Bi, Bt, P, D, group, lanes, 1);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
   const int64_t n = (int64_t)Bi * Bt;
-  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dsdot, 0, (size_t)Bi * P * 4, st));
-  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
-  allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, w.alpha, w.beta);
-  clipk::count_launches(1);
-  for (int i0 = 0; i0 < Bi; i0 += group) {
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(sh.dsdot, 0, (size_t)Bi * P * 4, st));
+  for (int l = 0; l < lanes; ++l)
+    CLIPK_CHECK_CUDA(cudaMemsetAsync(wl[l].dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
+  allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, sh.alpha, sh.beta);
+  count_launches(1);
+  LanePool* lp = nullptr;
+  if (lanes > 1) {
+    CLIPK_TRY(get_lanes(&lp));
+    CLIPK_TRY(fork_lanes(lp, lanes, st));
+  }
+  int gidx = 0;
+  for (int i0 = 0; i0 < Bi; i0 += group, ++gidx) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
+    const int l = gidx % lanes;
+    const ApWorkspace& w = wl[l];
+    cudaStream_t ls = lanes > 1 ? lp->st[l] : st;
     const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
     const float* rnV0 = rnV + (int64_t)i0 * P;
-    const float* alpha0 = w.alpha + (int64_t)i0 * Bt;
-    const float* beta0 = w.beta + (int64_t)i0 * Bt;
-    float* dsdot0 = w.dsdot + (int64_t)i0 * P;
+    const float* alpha0 = sh.alpha + (int64_t)i0 * Bt;
+    const float* beta0 = sh.beta + (int64_t)i0 * Bt;
+    float* dsdot0 = sh.dsdot + (int64_t)i0 * P;
     // K1 (recompute activations + scores)
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, true, nullptr, st));
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, true, nullptr, ls));
     // K2': G = alpha t^ - beta u
     {
       OperandDesc a, b;
       k2_operands(w, V0, gi, Bt, P, D, &a, &b);
       const int ks[1] = {Ppad / 64};
       epi::GOut::Params ep{alpha0, beta0, T, rnT, w.G, Bt, D};
-      CLIPK_TRY(launch_nd<epi::GOut, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, st));
+      CLIPK_TRY(launch_nd<epi::GOut, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
     }
     // K4: da = G V^T -> DS', E, dsdot
     {
@@ -252,10 +328,10 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       epi::DsOut::Params ep{w.A, w.S, rnV0, rnT, alpha0, w.DS, w.E, dsdot0, Bt, P, Ppad, act};
       int r;
       switch (pick_bn(Ppad)) {
-        case 256: r = launch_gemm<256, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
-        case 192: r = launch_gemm<192, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
-        case 128: r = launch_gemm<128, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
-        default: r = launch_gemm<64, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st); break;
+        case 256: r = launch_gemm<256, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
+        case 192: r = launch_gemm<192, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
+        case 128: r = launch_gemm<128, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
+        default: r = launch_gemm<64, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
       }
       CLIPK_TRY(r);
     }
@@ -269,28 +345,33 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       a.ptr = w.E; a.rows = Bt; a.k = Ppad; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
       a.sub_per_batch = spb;
       a.sub_total = gi;
+      a.reverse = 1;   // K4 walked upwards: take the last-written E first
       b.ptr = V0; b.mn_major = true; b.rows = D; b.k = P; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 0; b.smul = 1;
       const int ks[1] = {spb * (Ppad / 64)};
       const int ksub[1] = {Ppad / 64};
       epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
-      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, nsplit, ep, st));
+      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
     }
     // K6: dV_i = A_i^T G_i + DS'_i^T T - rnV^2 dsdot V
     {
       OperandDesc a[2], b[2];
       a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = Ppad; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
       a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
+      a[0].reverse = 1;
       b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
       b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
       a[1] = a[0]; a[1].ptr = w.DS;
       b[1].ptr = T; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
       const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
       epi::DvOut::Params ep{V0, rnV0, dsdot0, dV + (int64_t)i0 * P * D, P, D};
-      CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, st));
+      CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, ls));
     }
   }
-  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, kDthSplits, Bt, D, dT);
-  clipk::count_launches(1);
+  if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
+  DthSlabs slabs{};
+  for (int l = 0; l < lanes; ++l) slabs.p[l] = wl[l].dth;
+  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, slabs, lanes, kDthSplits, Bt, D, dT);
+  count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -299,27 +380,29 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
 
 extern "C" {
 
-size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int backward) {
-  clipk::ApWorkspace w{};
-  return clipk::ap_carve(&w, nullptr, Bi, Bt, P, D, group, backward);
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int backward) {
+  clipk::ApWorkspace w[clipk::kMaxLanes]{};
+  clipk::ApShared sh{};
+  if (lanes < 1 || lanes > clipk::kMaxLanes) return 0;
+  return clipk::ap_carve(w, &sh, nullptr, Bi, Bt, P, D, group, lanes, backward);
 }
 
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
                             float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
-                            int group, void* stream) {
+                            int group, int lanes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::allpairs_fwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
-                             act, c, rnV, rnT, num, usq, scores, workspace, ws_bytes, group,
+                             act, c, rnV, rnT, num, usq, scores, workspace, ws_bytes, group, lanes,
                              static_cast<cudaStream_t>(stream));
 }
 
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
                             const float* rnV, const float* rnT, const float* num, const float* usq,
                             const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
-                            void* stream) {
+                            int lanes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::allpairs_bwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
                              act, c, rnV, rnT, num, usq, dscores, static_cast<__nv_bfloat16*>(dV), dT, workspace,
-                             ws_bytes, group, static_cast<cudaStream_t>(stream));
+                             ws_bytes, group, lanes, static_cast<cudaStream_t>(stream));
 }
 }

@@ -109,12 +109,22 @@ def pacl_eval_scores(visual_proj, text_proj, c=100.0, activation="sigmoid"):
 
 
 # --------------------------------------------------------------------------------------------- all-pairs PACL
-def default_group(Bt, P, D, backward=True, budget_bytes=1 << 30):
-    """Images per group.  Measured on B200 (C2 shape): larger groups win (fewer, fuller launches) even once the
-    scratch no longer fits the 126 MB L2, so the default is bounded by a 1 GiB scratch budget, not by L2."""
-    ppad = (P + 63) // 64 * 64
-    per_image = Bt * ((4 * ppad * 2 + D * 2) if backward else ppad * 2)
-    return max(1, min(128, budget_bytes // max(per_image, 1)))
+def default_schedule(Bt, P, D, backward=True):
+    """(images per group, lanes).  See DESIGN.md "group scheduling": measured on B200 at the C2 shape."""
+    return _SCHEDULE["bwd" if backward else "fwd"]
+
+
+_SCHEDULE = {"fwd": (128, 1), "bwd": (128, 1)}
+
+
+def _resolve(group, Bi, Bt, P, D, backward):
+    if group is None:
+        g, lanes = default_schedule(Bt, P, D, backward)
+    elif isinstance(group, (tuple, list)):
+        g, lanes = group
+    else:
+        g, lanes = int(group), 1
+    return max(1, min(g, Bi)), max(1, min(lanes, 4))
 
 
 class _PaclAllPairs(torch.autograd.Function):
@@ -126,14 +136,13 @@ class _PaclAllPairs(torch.autograd.Function):
         Bi, P, D = Vb.shape
         Bt = Tb.shape[0]
         dev = Vb.device
-        g = group or default_group(Bt, P, D, backward=False)
-        g = min(g, Bi)
+        g, lanes = _resolve(group, Bi, Bt, P, D, False)
         rnV, rnT = _f32(Bi, P, device=dev), _f32(Bt, device=dev)
         num, usq, scores = _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev)
-        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, 0)
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_pacl_allpairs_fwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
-                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), ws.data_ptr(), nbytes, g,
+                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), ws.data_ptr(), nbytes, g, lanes,
                   _stream())
         ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq)
         ctx.cfg = (c, act, group, V.dtype, T.dtype)
@@ -146,22 +155,22 @@ class _PaclAllPairs(torch.autograd.Function):
         Bi, P, D = Vb.shape
         Bt = Tb.shape[0]
         dev = Vb.device
-        g = group or default_group(Bt, P, D, backward=True)
-        g = min(g, Bi)
+        g, lanes = _resolve(group, Bi, Bt, P, D, True)
         dscores = dscores.float().contiguous()
         dV = torch.empty_like(Vb)
         dT = _f32(Bt, D, device=dev)
-        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, 1)
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 1)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_pacl_allpairs_bwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
                   rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), dscores.data_ptr(), dV.data_ptr(), dT.data_ptr(),
-                  ws.data_ptr(), nbytes, g, _stream())
+                  ws.data_ptr(), nbytes, g, lanes, _stream())
         return dV.to(v_dtype), dT.to(t_dtype), None, None, None
 
 
 def pacl_scores(visual_proj, text_proj, c=1.0, activation="sigmoid", group=None):
     """All-pairs text-conditioned scores [Bi,Bt] = c * cos(pool(V_i | t_k), t_k) (bf16 tensor cores, fp32
-    accumulation).  Inputs are cast to bf16; gradients come back in the input dtypes."""
+    accumulation).  Inputs are cast to bf16; gradients come back in the input dtypes.
+    `group`: None (default schedule), images-per-group, or (images-per-group, lanes)."""
     return _PaclAllPairs.apply(visual_proj, text_proj, float(c), ACT[activation], group)
 
 

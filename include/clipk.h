@@ -76,17 +76,18 @@ int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P,
  * eval_pacl.py:53-57, :303-309 looped over images; patch_alignment pacl.py:120-133; pooling pacl.py:143-145).
  *   V bf16 [Bi,P,D], T bf16 [Bt,D]  ->  scores fp32 [Bi,Bt] = c * < n(sum_p sigmoid(10 s_ikp) V_ip), n(t_k) >
  * Saved for backward (caller-owned): rnV [Bi,P], rnT [Bt], num [Bi,Bt], usq [Bi,Bt].  The [Bi,Bt,P] activations
- * only ever exist for `group` images at a time inside `workspace` (tcgen05 GEMMs with fused epilogues).
+ * only ever exist for `group` images per lane inside `workspace` (tcgen05 GEMMs with fused epilogues); image groups
+ * are issued round-robin on `lanes` (1..4) internal streams forked from / joined to `stream` with events.
  * Backward: dscores [Bi,Bt] -> dV bf16 [Bi,P,D], dT fp32 [Bt,D] (gradient w.r.t. the raw T).
  */
-size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int backward);
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int backward);
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
                             float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
-                            int group, void* stream);
+                            int group, int lanes, void* stream);
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
                             const float* rnV, const float* rnT, const float* num, const float* usq,
                             const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
-                            void* stream);
+                            int lanes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Cross-entropy over a materialised fp32 matrix L [M,N] (leading dim ld): F.cross_entropy at pacl.py:509-512,

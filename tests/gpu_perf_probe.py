@@ -82,7 +82,7 @@ if __name__ == "__main__":
         gemm(576, 768, 1024, nb=64, a_mn=1, b_mn=1)
     if cmd in ("ap", "all"):
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-        groups = [int(x) for x in sys.argv[3:]] or [16, 32, 64]
+        groups = [tuple(int(y) for y in x.split(":")) if ":" in x else int(x) for x in sys.argv[3:]] or [16, 32, 64]
         for grp in groups:
             allpairs(B, 576, 768, grp)
     if cmd == "once":
@@ -99,3 +99,19 @@ if __name__ == "__main__":
         with torch.no_grad():
             Fk.pacl_scores(V, T, 10.0, "sigmoid", int(sys.argv[3]))
         torch.cuda.synchronize()
+    if cmd == "cpu":
+        import time
+        B = 1024
+        V = torch.randn(B, 576, 768, device="cuda").to(torch.bfloat16)
+        T = torch.randn(B, 768, device="cuda").to(torch.bfloat16)
+        for grp in (8, 16, 128):
+            with torch.no_grad():
+                Fk.pacl_scores(V, T, 10.0, "sigmoid", grp)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                Fk.pacl_scores(V, T, 10.0, "sigmoid", grp)
+                t1 = time.perf_counter()
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+            n = 2 * ((B + grp - 1) // grp)
+            print(f"group={grp}: host enqueue {1e3*(t1-t0):.2f} ms for {n} launches ({1e6*(t1-t0)/n:.1f} us/launch), total {1e3*(t2-t0):.2f} ms", flush=True)

@@ -99,6 +99,8 @@ def test_allpairs_groups_and_ones():
     e1 = _allpairs_case(7, 40, 100, 128, seed=41, group=2)
     e2 = _allpairs_case(7, 40, 100, 128, seed=41, group=7)
     assert max(e1) < 3e-2 and max(e2) < 3e-2
+    e4 = _allpairs_case(7, 40, 100, 128, seed=41, group=(2, 3))      # 3 internal lanes
+    assert max(e4) < 3e-2
     e3 = _allpairs_case(4, 40, 100, 128, seed=43, activation="ones")
     assert max(e3) < 3e-2
 
