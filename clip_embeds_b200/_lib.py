@@ -16,6 +16,7 @@ SIGNATURES = {
     "clipk_version": (c_int, []),
     "clipk_launch_count": (ctypes.c_ulonglong, []),
     "clipk_check_device": (c_int, []),
+    "clipk_trace_dump": (c_int, []),
     "clipk_gemm_bf16": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_i64, c_int,
                                 c_int, c_int, c_int, c_int, c_f32, c_int, c_vp]),
     "clipk_pacl_paired_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,

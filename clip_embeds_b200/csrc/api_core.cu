@@ -1,6 +1,10 @@
 // Error reporting, device gate and TMA tensor-map construction.
 #include <atomic>
 #include <mutex>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdlib.h>
 
 #include <cudaTypedefs.h>
 
@@ -11,6 +15,34 @@ namespace clipk {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- optional per-launch event trace (CLIPK_TRACE=1): diagnostic only, never enabled by the product path
+struct TraceRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_trace_mu;
+static std::vector<TraceRec> g_trace;
+bool trace_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CLIPK_TRACE");
+    on = (e != nullptr && e[0] != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+void trace_begin(const char* name, cudaStream_t st) {
+  TraceRec r{name, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  g_trace.push_back(r);
+}
+void trace_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (!g_trace.empty()) cudaEventRecord(g_trace.back().e1, st);
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -119,4 +151,30 @@ const char* clipk_last_error(void) { return clipk::g_err; }
 int clipk_version(void) { return 100; }
 unsigned long long clipk_launch_count(void) { return clipk::g_launches.load(std::memory_order_relaxed); }
 int clipk_check_device(void) { return clipk::check_device(); }
+int clipk_trace_dump(void) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return CLIPK_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(clipk::g_trace_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  double tot = 0;
+  for (auto& r : clipk::g_trace) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    std::string n(r.name);
+    size_t w = n.find("[with ");
+    if (w != std::string::npos) n = n.substr(w + 6);
+    if (n.size() > 100) n.resize(100);
+    agg[n].first += 1;
+    agg[n].second += ms;
+    tot += ms;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  clipk::g_trace.clear();
+  for (auto& kv : agg)
+    printf("trace %9.3f ms %5d launches avg %8.1f us %5.1f%%  %s\n", kv.second.second, kv.second.first,
+           1e3 * kv.second.second / kv.second.first, 100.0 * kv.second.second / (tot > 0 ? tot : 1), kv.first.c_str());
+  printf("trace total %.3f ms\n", tot);
+  fflush(stdout);
+  return 0;
+}
 }

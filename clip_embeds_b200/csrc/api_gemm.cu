@@ -10,6 +10,12 @@ static int gemm_dispatch_out(const OperandDesc& a, const OperandDesc& b, int kst
                              cudaStream_t st) {
   int ks[1] = {ksteps};
   int ksub[1] = {ksteps};
+  if (out_dtype == CLIPK_BF16 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0 &&
+      (batches == 1 || strideC % 8 == 0)) {
+    // 16-byte aligned rows: the tile leaves the SM through the engine's TMA-store path
+    epi::StoreTma::Params ep{{C, ldc, batches > 1 ? strideC : (int64_t)M * ldc, M, N, batches}, alpha};
+    return launch_gemm<BN, A_MN, B_MN, epi::StoreTma>(&a, &b, 1, ks, ksub, M, N, batches, ep, st);
+  }
   if (out_dtype == CLIPK_BF16) {
     typename epi::Store<true>::Params ep{C, ldc, strideC, M, N, alpha, 0};
     return launch_gemm<BN, A_MN, B_MN, epi::Store<true>>(&a, &b, 1, ks, ksub, M, N, batches, ep, st);

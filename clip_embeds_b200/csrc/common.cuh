@@ -17,7 +17,10 @@ namespace clipk {
 void set_error(const char* fmt, ...);          // thread-local message returned by clipk_last_error()
 int check_device();                            // 0 if the current device is sm_100 (B200), else CLIPK_ERR_ARCH
 int sm_count();                                // SM count of the current device
-void count_launches(int n);                    // bump the library-wide kernel-launch counter (clipk_launch_count)
+void count_launches(int n);
+bool trace_enabled();                          // CLIPK_TRACE=1: record CUDA events around every engine launch
+void trace_begin(const char* name, cudaStream_t st);
+void trace_end(cudaStream_t st);                    // bump the library-wide kernel-launch counter (clipk_launch_count)
 
 #define CLIPK_CHECK_CUDA(expr)                                                                       \
   do {                                                                                               \
@@ -66,7 +69,9 @@ struct OperandDesc {
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const int* ksteps, const int* ksub,
                 int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t stream) {
-  using L = eng::SmemLayout<BN>;
+  constexpr bool kDual = eng::epi_dual<Epi>::value;
+  constexpr bool kTmaOut = eng::epi_tma_out<Epi>::value;
+  using L = eng::SmemLayout<BN, kDual, kTmaOut>;
   eng::OperandMaps maps;
   memset(&maps, 0, sizeof(maps));
   eng::Problem pb;
@@ -96,6 +101,15 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
       CLIPK_TRY(make_tmap_bf16(&maps.b[q], b[q].ptr, b[q].rows, b[q].k, b[q].batch, b[q].ld * 2, b[q].batch_stride * 2, 64));
     }
   }
+  if constexpr (kDual) {      // second A operand (shares pair 0's B): a[1] describes it, num_pairs stays 1
+    pb.a_bmul[1] = a[1].bmul;
+    CLIPK_TRY(make_tmap_bf16(&maps.a[1], a[1].ptr, a[1].k, a[1].rows, a[1].batch, a[1].ld * 2, a[1].batch_stride * 2, eng::BM));
+  }
+  if constexpr (kTmaOut) {
+    const eng::OutDesc& o = ep.out;
+    CLIPK_TRY(make_tmap_bf16(&maps.out, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, (uint64_t)o.batches, (uint64_t)o.ld * 2,
+                             (uint64_t)o.stride * 2, eng::BM));
+  }
   const int total = pb.batches * pb.tiles_m * pb.tiles_n;
   if (total <= 0) return 0;
   auto kern = eng::gemm_kernel<BN, A_MN, B_MN, Epi>;
@@ -107,7 +121,10 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
     attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   const int grid = total < sm_count() ? total : sm_count();
+  const bool tr = trace_enabled();
+  if (tr) trace_begin(__PRETTY_FUNCTION__, stream);
   kern<<<grid, eng::kThreads, L::kTotal, stream>>>(maps, pb, ep);
+  if (tr) trace_end(stream);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -2,6 +2,7 @@
 // consecutive fp32 accumulator columns [n, n+32) of that row.
 #pragma once
 #include "../../include/clipk.h"
+#include "gemm_engine.cuh"
 #include "ptx.cuh"
 
 namespace epi {
@@ -170,16 +171,34 @@ __device__ __forceinline__ void store_bf16x32_exact(__nv_bfloat16* dst, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------ plain bf16 store via TMA
+// C[b][m][n] = bf16(alpha * acc), written by the engine's TMA-store path (needs 16-byte aligned rows)
+struct StoreTma {
+  static constexpr bool kTmaOut = true;
+  struct Params {
+    eng::OutDesc out;
+    float alpha;
+  };
+  Params p;
+  __device__ explicit StoreTma(const Params& pp) : p(pp) {}
+  __device__ void tile_begin(int, int, int) {}
+  __device__ void chunk(int, int, int, float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1
 // acc[m=text k][n=patch p] = <T_k, V_ip> (raw).  s = acc * rnT[k] * rnV[i,p];  a = sigmoid(10 s)  (pacl.py:133)
-// writes A (bf16, zero in the pad columns), optionally S (fp16), and num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
-template <bool WITH_S>
+// output (TMA store): A bf16 [batch][M][Ppad], zero in the pad columns;
+// side output: num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
 struct PaclAct {
+  static constexpr bool kTmaOut = true;
   struct Params {
+    eng::OutDesc out;   // A
     const float* rnV;   // [batch][P]
     const float* rnT;   // [M]
-    __nv_bfloat16* A;   // [batch][M][Ppad]
-    __half* S;          // [batch][M][Ppad] (WITH_S only)
     float* num;         // [batch][M] or nullptr
     int M, P, Ppad, act;
   };
@@ -191,13 +210,11 @@ struct PaclAct {
     rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
     rt5 = 5.f * rt;
   }
-  __device__ void chunk(int b, int m, int n, float* v) {
-    if (n >= p.Ppad) return;                       // warp-uniform
+  __device__ void chunk(int b, int, int n, float* v) {
     const int lane = (int)ptx::lane_id();
     // one coalesced load of the 32 patch norms of this chunk, broadcast by shuffle (branch-free inner loop)
     const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
     const bool ones = p.act == CLIPK_ACT_ONES;
-    float s[WITH_S ? 32 : 1];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float rnj = __shfl_sync(0xffffffffu, rn_l, j);
@@ -207,14 +224,8 @@ struct PaclAct {
       float a = ones ? 1.f : bf16_round(fmaf(0.5f, t, 0.5f));
       a = (n + j < p.P) ? a : 0.f;
       acc = fmaf(a, v[j], acc);                    // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
-      if constexpr (WITH_S) s[j] = x * rt;
       v[j] = a;
     }
-    if (m >= p.M) return;
-    const int valid = min(32, p.Ppad - n);
-    const int64_t off = ((int64_t)b * p.M + m) * p.Ppad + n;
-    store_bf16x32_exact(p.A + off, v, valid);
-    if constexpr (WITH_S) store_f16x32(p.S + off, s, valid);
   }
   __device__ void tile_end(int b, int m, int, int, int) {
     if (p.num != nullptr && m < p.M) atomicAdd(p.num + (int64_t)b * p.M + m, acc * rt);
@@ -244,101 +255,87 @@ struct Usq {
 };
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (bwd)
-// acc = u_ik[d];  G_ik = alpha_ik t^_k - beta_ik u_ik   (grad wrt the un-normalised pooled vector), stored bf16
-struct GOut {
+// acc = u_ik[d].  The gradient w.r.t. the un-normalised pooled vector is G_ik = alpha_ik t^_k - beta_ik u_ik; only its
+// u-part  Gn_ik = -beta_ik u_ik  is materialised (bf16, TMA store): the t^ part is folded analytically into the
+// consumers (DsDual adds alpha <t^,V>; the dV GEMM uses E^T T^ which already contains alpha a t^).
+struct GNeg {
+  static constexpr bool kTmaOut = true;
   struct Params {
-    const float* alpha;        // [batch][M]
+    eng::OutDesc out;          // Gn [batch][M][N]
     const float* beta;         // [batch][M]
-    const __nv_bfloat16* T;    // [M][N]
-    const float* rnT;          // [M]
-    __nv_bfloat16* G;          // [batch][M][N]
-    int M, N;
+    int M;
   };
   Params p;
-  float al, be;
-  __device__ explicit GOut(const Params& pp) : p(pp), al(0.f), be(0.f) {}
-  __device__ void tile_begin(int b, int m, int) {
-    if (m < p.M) {
-      al = __ldg(p.alpha + (int64_t)b * p.M + m) * __ldg(p.rnT + m);
-      be = __ldg(p.beta + (int64_t)b * p.M + m);
-    }
-  }
-  __device__ void chunk(int b, int m, int n, float* v) {
-    if (m >= p.M || n >= p.N) return;
-    const int valid = min(32, p.N - n);
-    float t[32];
-    load_bf16x32(p.T + (int64_t)m * p.N + n, t, valid);
+  float nb;
+  __device__ explicit GNeg(const Params& pp) : p(pp), nb(0.f) {}
+  __device__ void tile_begin(int b, int m, int) { nb = (m < p.M) ? -__ldg(p.beta + (int64_t)b * p.M + m) : 0.f; }
+  __device__ void chunk(int, int, int, float* v) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = al * t[j] - be * v[j];
-    store_bf16x32(p.G + ((int64_t)b * p.M + m) * p.N + n, v, valid);
+    for (int j = 0; j < 32; ++j) v[j] *= nb;
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
-// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM3 (bwd)
-// acc = da_ikp = <G_ik, V_ip>.  ds = da * 10 a (1 - a);
-//   DS'[i,k,p] = ds * rnV[i,p] * rnT[k]      (operand of dV += DS'^T T)
-//   E  [i,k,p] = ds * rnV[i,p] + alpha_ik a  (operand of dt^ += E V; the alpha term is the direct d score / d t^)
-//   dsdot[i,p] += sum_k ds * s               (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
-struct DsOut {
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1+GEMM3 (bwd)
+// Dual accumulators over the same V tile:  x = <T_k, V_ip> (raw score, recomputed)  and  d = <Gn_ik, V_ip>.
+//   s  = x rnT rnV,  a = sigmoid(10 s)                              (recomputed in registers: never re-read from HBM)
+//   da = alpha_ik rnT_k x + d   ( = <G_ik, V_ip> ),   ds = da * 10 a (1 - a)
+//   E[i,k,p] = ds * rnV[i,p] + alpha_ik a     (TMA store; operand of dt^ += E V  and of dV += E^T T^)
+//   dsdot[i,p] += sum_k ds * s                (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
+struct DsDual {
+  static constexpr bool kTmaOut = true;
+  static constexpr bool kDual = true;
   struct Params {
-    const __nv_bfloat16* A;  // [batch][M][Ppad]
-    const __half* S;         // [batch][M][Ppad]
+    eng::OutDesc out;        // E [batch][M][Ppad]
     const float* rnV;        // [batch][P]
     const float* rnT;        // [M]
     const float* alpha;      // [batch][M]
-    __nv_bfloat16* DS;       // [batch][M][Ppad]
-    __nv_bfloat16* E;        // [batch][M][Ppad]
     float* dsdot;            // [batch][P]
     int M, P, Ppad, act;
   };
   Params p;
   float rt, al;
-  __device__ explicit DsOut(const Params& pp) : p(pp), rt(0.f), al(0.f) {}
+  __device__ explicit DsDual(const Params& pp) : p(pp), rt(0.f), al(0.f) {}
   __device__ void tile_begin(int b, int m, int) {
     rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
     al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f;
   }
-  __device__ void chunk(int b, int m, int n, float* v) {
-    if (n >= p.Ppad) return;     // warp-uniform
-    const bool row_ok = m < p.M;
+  __device__ void chunk2(int b, int m, int n, float* x, float* d) {
     const int lane = (int)ptx::lane_id();
-    const int valid = min(32, p.Ppad - n);
-    const int64_t off = ((int64_t)b * p.M + (row_ok ? m : 0)) * p.Ppad + n;
-    float a[32], s[32];
-    load_bf16x32(p.A + off, a, valid);             // rows >= M re-read row 0 (masked below)
-    load_f16x32(p.S + off, s, valid);
     const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
-    const float gate = (row_ok && p.act != CLIPK_ACT_ONES) ? 10.f : 0.f;
-    float e[32];
+    const bool ones = p.act == CLIPK_ACT_ONES;
+    const float gate = (m < p.M && !ones) ? 10.f : 0.f;
+    const float art = al * rt;
+    const float rt5 = 5.f * rt;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float rnj = __shfl_sync(0xffffffffu, rn_l, j);      // 0 for p >= P: masks the pad columns
-      const float ds = v[j] * gate * a[j] * (1.f - a[j]);
+      const float xs = x[j] * rnj;
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xs * rt5));
+      const float a = ones ? 1.f : bf16_round(fmaf(0.5f, t, 0.5f));
+      const float da = fmaf(art, x[j], d[j]);
+      const float ds = da * gate * a * (1.f - a);
       const float dsv = ds * rnj;
-      e[j] = (n + j < p.P) ? fmaf(al, a[j], dsv) : 0.f;
-      v[j] = dsv * rt;
-      s[j] = (n + j < p.P) ? ds * s[j] : 0.f;
+      x[j] = (n + j < p.P) ? fmaf(al, a, dsv) : 0.f;            // E
+      d[j] = ds * xs * rt;                                       // ds * s  (0 in pad columns / invalid rows)
     }
-    if (row_ok) {
-      store_bf16x32(p.DS + off, v, valid);
-      store_bf16x32(p.E + off, e, valid);
-    }
-    const float cs = ptx::warp_colsum32(s);   // lane j: sum over this warp's 32 rows of column n + j
-    const int col = n + (int)ptx::lane_id();
+    const float cs = ptx::warp_colsum32(d);   // lane j: sum over this warp's 32 rows of column n + j
+    const int col = n + lane;
     if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, dV (bwd)
-// acc[m=patch p][n=d] = sum_k a_ikp G_ik[d] + sum_k DS'_ikp T_k[d];  dV_ip = acc - rnV_ip^2 dsdot_ip V_ip
+// acc[m=patch p][n=d] = sum_k a_ikp Gn_ik[d] + sum_k E_ikp T^_k[d];  dV_ip = acc - rnV_ip^2 dsdot_ip V_ip  (TMA store)
 struct DvOut {
+  static constexpr bool kTmaOut = true;
   struct Params {
+    eng::OutDesc out;         // dV [batch][M][N]
     const __nv_bfloat16* V;   // [batch][M][N]
     const float* rnV;         // [batch][M]
     const float* dsdot;       // [batch][M]
-    __nv_bfloat16* dV;        // [batch][M][N]
     int M, N;
   };
   Params p;
@@ -358,7 +355,6 @@ struct DvOut {
     load_bf16x32(p.V + off, x, valid);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(-coef, x[j], v[j]);
-    store_bf16x32(p.dV + off, v, valid);
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };

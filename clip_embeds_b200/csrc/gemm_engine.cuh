@@ -15,16 +15,44 @@
 // Operands may be K-major (k contiguous in global memory: tensor map dims (k, row, batch)) or MN-major (row index
 // contiguous: tensor map dims (row, k, batch)); both land in shared memory as 128-byte swizzled rows, see
 // ptx::umma_desc.  Tiles: BM=128 x BN x BK=64, kStages-deep ring of (A,B) stages.
+//
+// Two optional engine features are selected by traits of the epilogue functor:
+//   Epi::kTmaOut = true : the functor leaves one bf16 output row-chunk per call in v[]; the engine packs it into a
+//                         128B-swizzled [128 x 64] shared-memory slab (double-buffered) and one elected thread writes
+//                         the slab with cp.async.bulk.tensor (TMA store: full-line coalesced writes, rows / columns
+//                         outside the output extent are clipped by the tensor map).
+//   Epi::kDual = true   : TWO A operands share one B operand and accumulate into two TMEM accumulators
+//                         (acc0 = A0 B^T, acc1 = A1 B^T); the functor's chunk2() sees both (BN <= 128).
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace eng {
+
+template <class E, class = void>
+struct epi_tma_out : std::false_type {};
+template <class E>
+struct epi_tma_out<E, std::void_t<decltype(E::kTmaOut)>> : std::bool_constant<E::kTmaOut> {};
+template <class E, class = void>
+struct epi_dual : std::false_type {};
+template <class E>
+struct epi_dual<E, std::void_t<decltype(E::kDual)>> : std::bool_constant<E::kDual> {};
+
+// description of the TMA-stored output (member `out` of Epi::Params when Epi::kTmaOut)
+struct OutDesc {
+  void* ptr;
+  int64_t ld, stride;      // elements (2-byte): row stride, batch stride
+  int rows, cols, batches; // extents: rows / cols beyond them are clipped
+};
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps (2 per TMEM lane quadrant / SMSP)
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
+constexpr int kEpiBarId = 1;       // named barrier of the 8 epilogue warps (TMA-out staging)
+constexpr int kSmemBudget = 227 * 1024;
 // L2-prefetch distance of the producer (k-steps ahead of the load cursor).  Measured on B200: prefetching doubles the
 // TMA request rate and costs 20-25% on every shape (4096^3: 1290 -> 980 TFLOP/s), so it is disabled (0).
 constexpr int kPrefetchDist = 0;
@@ -32,6 +60,7 @@ constexpr int kPrefetchDist = 0;
 struct OperandMaps {
   CUtensorMap a[2];
   CUtensorMap b[2];
+  CUtensorMap out;
 };
 
 struct Problem {
@@ -49,14 +78,20 @@ struct Problem {
                              // launch first touches what the previous one wrote last (still L2-resident)
 };
 
-template <int BN>
+template <int BN, bool DUAL = false, bool TMA_OUT = false>
 struct SmemLayout {
-  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kA1Bytes = BM * BK * 2;
+  static constexpr int kABytes = kA1Bytes * (DUAL ? 2 : 1);
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int kOutSlabBytes = BM * 128;                  // [128 rows][64 bf16]
+  static constexpr int kOutBytes = TMA_OUT ? 2 * kOutSlabBytes : 0;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+  static constexpr int kAvail = kSmemBudget - 1024 /*align slack*/ - kBarrierBytes - kOutBytes;
+  static constexpr int kStagesRaw = kAvail / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 3, "smem ring too shallow");
 };
 
 __device__ __forceinline__ int ksteps_of(const Problem& pb, int q, int b) {
@@ -69,11 +104,16 @@ __device__ __forceinline__ int ksteps_of(const Problem& pb, int q, int b) {
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const typename Epi::Params ep) {
-  using L = SmemLayout<BN>;
+  constexpr bool DUAL = epi_dual<Epi>::value;
+  constexpr bool TMA_OUT = epi_tma_out<Epi>::value;
+  static_assert(!DUAL || (BN <= 128 && !A_MN), "dual accumulators: BN <= 128, K-major A operands");
+  constexpr int kAccCols = DUAL ? 2 * BN : BN;          // TMEM columns of one accumulator buffer
+  using L = SmemLayout<BN, DUAL, TMA_OUT>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint8_t* out_smem = smem + kStages * L::kStageBytes;  // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_smem + L::kOutBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
@@ -89,6 +129,8 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       ptx::prefetch_tmap(&maps.a[q]);
       ptx::prefetch_tmap(&maps.b[q]);
     }
+    if constexpr (DUAL) ptx::prefetch_tmap(&maps.a[1]);
+    if constexpr (TMA_OUT) ptx::prefetch_tmap(&maps.out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -186,7 +228,11 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
         ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-        if constexpr (!A_MN) {
+        if constexpr (DUAL) {
+          const int ab1 = ld.b * pb.a_bmul[1];
+          ptx::tma_load_3d(sa, &maps.a[0], &full_bar[stage], k0, ld.m0, ab);
+          ptx::tma_load_3d(sa + L::kA1Bytes, &maps.a[1], &full_bar[stage], k0, ld.m0, ab1);
+        } else if constexpr (!A_MN) {
           ptx::tma_load_3d(sa, &maps.a[ld.q], &full_bar[stage], k0, ld.m0, ab);
         } else {
 #pragma unroll
@@ -218,7 +264,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
         const int b = pb.reverse ? pb.batches - 1 - bl0 : bl0;
         ptx::mbar_wait(&tempty_bar[buf], bphase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t tmem_d = tmem_base + buf * kAccCols;
         uint32_t accum = 0;
         for (int q = 0; q < pb.num_pairs; ++q) {
           const int nks = ksteps_of(pb, q, b);
@@ -233,6 +279,10 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
               const uint64_t ad = A_MN ? ptx::umma_desc(sa + kk * 2048, 8192, 1024) : ptx::umma_desc(sa + kk * 32, 16, 1024);
               const uint64_t bd = B_MN ? ptx::umma_desc(sb + kk * 2048, 8192, 1024) : ptx::umma_desc(sb + kk * 32, 16, 1024);
               ptx::mma_bf16_ss(tmem_d, ad, bd, idesc, accum);
+              if constexpr (DUAL) {
+                const uint64_t ad1 = ptx::umma_desc(sa + L::kA1Bytes + kk * 32, 16, 1024);
+                ptx::mma_bf16_ss(tmem_d + BN, ad1, bd, idesc, accum);
+              }
               accum = 1;
             }
             ptx::mma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
@@ -246,8 +296,10 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
     // ------------------------------------------------------------------ epilogue
     const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read
     const int half = (warp - kEpiWarp0) >> 2;      // 0/1: which alternate chunks this warp takes
+    const bool issuer = (warp == kEpiWarp0) && (lane == 0);   // the one thread that owns the TMA-store bulk groups
     Epi epi(ep);
     int it = 0;
+    int slab = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int bl = tile / tiles_per_batch;
       const int rem = tile - bl * tiles_per_batch;
@@ -260,17 +312,56 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       ptx::tc_fence_after();
       const int m = m0 + q4 * 32 + lane;
       epi.tile_begin(b, m, n0);
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * kAccCols;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int j = 0; j < BN / 64; ++j) {
+        const int c = 2 * j + half;
         float v[32];
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * BN + c * 32, v);
-        ptx::tmem_ld_wait();
-        epi.chunk(b, m, n0 + c * 32, v);
+        ptx::tmem_ld_32x32(tacc + c * 32, v);
+        if constexpr (DUAL) {
+          float v1[32];
+          ptx::tmem_ld_32x32(tacc + BN + c * 32, v1);
+          ptx::tmem_ld_wait();
+          if (j == BN / 64 - 1) {                  // accumulator drained: hand the TMEM buffer back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+          }
+          epi.chunk2(b, m, n0 + c * 32, v, v1);
+        } else {
+          ptx::tmem_ld_wait();
+          if (j == BN / 64 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+          }
+          epi.chunk(b, m, n0 + c * 32, v);
+        }
+        if constexpr (TMA_OUT) {
+          uint8_t* sbuf = out_smem + (slab & 1) * L::kOutSlabBytes;
+          if (issuer) ptx::bulk_wait_group_read<1>();        // the store that last used this slab has read it
+          ptx::named_bar_sync(kEpiBarId, kEpiWarps * 32);
+          const int r = q4 * 32 + lane;
+          const uint32_t rowbase = ptx::smem_u32(sbuf) + r * 128;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t addr = rowbase + ((static_cast<uint32_t>(half * 4 + t) ^ static_cast<uint32_t>(r & 7)) << 4);
+            ptx::st_shared_v4(addr, ptx::pack_bf16x2(v[8 * t + 0], v[8 * t + 1]), ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]),
+                              ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]), ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(kEpiBarId, kEpiWarps * 32);
+          if (issuer) {
+            ptx::tma_store_3d(&maps.out, sbuf, n0 + j * 64, m0, b);
+            ptx::bulk_commit_group();
+          }
+          ++slab;
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
       epi.tile_end(b, m, n0, rem % pb.tiles_n, half);
+    }
+    if constexpr (TMA_OUT) {
+      if (issuer) ptx::bulk_wait_group<0>();
     }
   }
 

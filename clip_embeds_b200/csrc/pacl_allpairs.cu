@@ -11,12 +11,15 @@
 // is re-used by every group (sized to stay L2-resident), so the [Bi, Bt, P] tensor is never materialised in HBM and
 // only O(Bi*Bt) + O(Bi*P) statistics are saved for backward (recompute, flash-style).
 //
-//  forward :  K1  A = act(T V_i^T)            (epilogue PaclAct: also num = <u, t^>)
+//  forward :  K1  A = act(T V_i^T)            (epilogue PaclAct: also num = <u, t^>; A leaves the SM by TMA store)
 //             K2  u = A V_i  -> usq = |u|^2   (epilogue Usq: u never stored)
-//  backward:  K1  (recompute A, + S)          K2' G = alpha t^ - beta u          (epilogue GOut)
-//             K4  da = G V_i^T -> DS', E, dsdot (epilogue DsOut)
+//  backward:  K1  (recompute A)               K2' Gn = -beta u                   (epilogue GNeg, TMA store)
+//             K4  dual accumulators x = T V_i^T (recomputed), d = Gn V_i^T -> E, dsdot   (epilogue DsDual: reads no
+//                 activation tensor back from memory)
 //             K5  dt^ += E V                  (K folds (image, patch); fp32 accumulate)
-//             K6  dV_i = A^T G + DS'^T T - rnV^2 dsdot V   (two operand pairs, epilogue DvOut)
+//             K6  dV_i = A^T Gn + E^T T^ - rnV^2 dsdot V      (two operand pairs, epilogue DvOut, TMA store)
+//  with G_ik = alpha_ik t^_k - beta_ik u_ik the gradient w.r.t. the pooled vector, E = ds rnV + alpha a and
+//  T^ = bf16(T rnT): sum_k a G = E-part + A^T Gn because alpha a t^ is already inside E^T T^.
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_util.cuh"
@@ -41,6 +44,20 @@ __global__ void rownorm_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t
   }
   acc = ptx::warp_sum(acc);
   if (lane == 0) rn[row] = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+}
+
+// T^ = bf16(T * rnT)   (operand of dV += E^T T^)
+__global__ void that_bf16_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT, int Bt, int D,
+                                 __nv_bfloat16* __restrict__ That) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= (int64_t)Bt * D) return;
+  const float r = rnT[i / D];
+  float v[8];
+  simt::load8<__nv_bfloat16>(T + i, v);
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(v[j] * r);
+  *reinterpret_cast<uint4*>(That + i) = *reinterpret_cast<const uint4*>(o);
 }
 
 __global__ void allpairs_scores_kernel(const float* __restrict__ num, const float* __restrict__ usq, int64_t n, float c,
@@ -119,13 +136,13 @@ static int get_lanes(LanePool** out) {
 }
 
 struct ApWorkspace {      // per-lane scratch
-  __nv_bfloat16 *A, *G, *DS, *E;
-  __half* S;
+  __nv_bfloat16 *A, *G, *E;
   float* dth;             // [kDthSplits][Bt][D] fp32 split-K slabs of this lane
 };
 
 struct ApShared {
   float *dsdot, *alpha, *beta, *dth;
+  __nv_bfloat16* That;
 };
 // layout: [lanes x per-lane scratch][shared per-call arrays]
 static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt, int P, int D, int group, int lanes,
@@ -141,8 +158,6 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
   for (int l = 0; l < lanes; ++l) {
     w[l].A = static_cast<__nv_bfloat16*>(take(act));
     if (backward) {
-      w[l].S = static_cast<__half*>(take(act));
-      w[l].DS = static_cast<__nv_bfloat16*>(take(act));
       w[l].E = static_cast<__nv_bfloat16*>(take(act));
       w[l].G = static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
       w[l].dth = static_cast<float*>(take((size_t)kDthSplits * Bt * D * 4));
@@ -152,6 +167,7 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
     sh->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
     sh->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
     sh->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    sh->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
     sh->dth = w[0].dth;
   }
   return off;
@@ -169,28 +185,18 @@ static int pick_bn(int n) {
 
 // K1: A = act(T V^T) for `gi` images starting at V0.
 static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, int Bt, int P, int D, int act,
-                     const float* rnV0, const float* rnT, const ApWorkspace& w, bool with_s, float* num0,
-                     cudaStream_t st) {
+                     const float* rnV0, const float* rnT, const ApWorkspace& w, float* num0, cudaStream_t st) {
   const int Ppad = round_up(P, 64);
   OperandDesc a, b;
   a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
   b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
   const int ks[1] = {(D + 63) / 64};
-  if (with_s) {
-    epi::PaclAct<true>::Params ep{rnV0, rnT, w.A, w.S, num0, Bt, P, Ppad, act};
-    switch (pick_bn(Ppad)) {
-      case 256: return launch_gemm<256, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-      case 192: return launch_gemm<192, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-      case 128: return launch_gemm<128, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-      default: return launch_gemm<64, false, false, epi::PaclAct<true>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    }
-  }
-  epi::PaclAct<false>::Params ep{rnV0, rnT, w.A, nullptr, num0, Bt, P, Ppad, act};
+  epi::PaclAct::Params ep{{w.A, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, num0, Bt, P, Ppad, act};
   switch (pick_bn(Ppad)) {
-    case 256: return launch_gemm<256, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 192: return launch_gemm<192, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 128: return launch_gemm<128, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    default: return launch_gemm<64, false, false, epi::PaclAct<false>>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 256: return launch_gemm<256, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 192: return launch_gemm<192, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 128: return launch_gemm<128, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    default: return launch_gemm<64, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
   }
 }
 
@@ -262,7 +268,7 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     const int l = gidx % lanes;
     cudaStream_t ls = lanes > 1 ? lp->st[l] : st;
     const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w[l], false, num + (int64_t)i0 * Bt, ls));
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w[l], num + (int64_t)i0 * Bt, ls));
     OperandDesc a, b;
     k2_operands(w[l], V0, gi, Bt, P, D, &a, &b);
     const int ks[1] = {Ppad / 64};
@@ -292,7 +298,8 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   for (int l = 0; l < lanes; ++l)
     CLIPK_CHECK_CUDA(cudaMemsetAsync(wl[l].dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
   allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, sh.alpha, sh.beta);
-  count_launches(1);
+  that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
+  count_launches(2);
   LanePool* lp = nullptr;
   if (lanes > 1) {
     CLIPK_TRY(get_lanes(&lp));
@@ -309,31 +316,29 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     const float* alpha0 = sh.alpha + (int64_t)i0 * Bt;
     const float* beta0 = sh.beta + (int64_t)i0 * Bt;
     float* dsdot0 = sh.dsdot + (int64_t)i0 * P;
-    // K1 (recompute activations + scores)
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, true, nullptr, ls));
-    // K2': G = alpha t^ - beta u
+    // K1 (recompute activations)
+    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, nullptr, ls));
+    // K2': Gn = -beta u
     {
       OperandDesc a, b;
       k2_operands(w, V0, gi, Bt, P, D, &a, &b);
       const int ks[1] = {Ppad / 64};
-      epi::GOut::Params ep{alpha0, beta0, T, rnT, w.G, Bt, D};
-      CLIPK_TRY(launch_nd<epi::GOut, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+      epi::GNeg::Params ep{{w.G, D, (int64_t)Bt * D, Bt, D, gi}, beta0, Bt};
+      CLIPK_TRY(launch_nd<epi::GNeg, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
     }
-    // K4: da = G V^T -> DS', E, dsdot
+    // K4 (dual): x = T V^T (recomputed), d = Gn V^T  ->  E, dsdot
     {
-      OperandDesc a, b;
-      a.ptr = w.G; a.rows = Bt; a.k = D; a.ld = D; a.batch = gi; a.batch_stride = (int64_t)Bt * D; a.bmul = 1;
+      OperandDesc a[2], b;
+      a[0].ptr = T; a[0].rows = Bt; a[0].k = D; a[0].ld = D; a[0].batch = 1; a[0].bmul = 0;
+      a[1].ptr = w.G; a[1].rows = Bt; a[1].k = D; a[1].ld = D; a[1].batch = gi; a[1].batch_stride = (int64_t)Bt * D; a[1].bmul = 1;
       b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
       const int ks[1] = {(D + 63) / 64};
-      epi::DsOut::Params ep{w.A, w.S, rnV0, rnT, alpha0, w.DS, w.E, dsdot0, Bt, P, Ppad, act};
-      int r;
-      switch (pick_bn(Ppad)) {
-        case 256: r = launch_gemm<256, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
-        case 192: r = launch_gemm<192, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
-        case 128: r = launch_gemm<128, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
-        default: r = launch_gemm<64, false, false, epi::DsOut>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls); break;
+      epi::DsDual::Params ep{{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, alpha0, dsdot0, Bt, P, Ppad, act};
+      if (Ppad % 128 == 0 || Ppad > 64) {
+        CLIPK_TRY(launch_gemm<128, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls));
+      } else {
+        CLIPK_TRY(launch_gemm<64, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls));
       }
-      CLIPK_TRY(r);
     }
     // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch; split-K over images so that
     //     nsplit x tiles CTAs are busy; each split accumulates into its own fp32 slab, summed in the finalize)
@@ -352,7 +357,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
       CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
     }
-    // K6: dV_i = A_i^T G_i + DS'_i^T T - rnV^2 dsdot V
+    // K6: dV_i = A_i^T Gn_i + E_i^T T^ - rnV^2 dsdot V
     {
       OperandDesc a[2], b[2];
       a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = Ppad; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
@@ -360,10 +365,10 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       a[0].reverse = 1;
       b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
       b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
-      a[1] = a[0]; a[1].ptr = w.DS;
-      b[1].ptr = T; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
+      a[1] = a[0]; a[1].ptr = w.E;
+      b[1].ptr = sh.That; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
       const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
-      epi::DvOut::Params ep{V0, rnV0, dsdot0, dV + (int64_t)i0 * P * D, P, D};
+      epi::DvOut::Params ep{{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi}, V0, rnV0, dsdot0, P, D};
       CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, ls));
     }
   }

@@ -41,6 +41,9 @@ int clipk_version(void);
 unsigned long long clipk_launch_count(void);
 /* 0 when the current CUDA device can run the kernels (compute capability 10.x), else CLIPK_ERR_ARCH. */
 int clipk_check_device(void);
+/* Diagnostic: with CLIPK_TRACE=1 in the environment every engine launch is bracketed by CUDA events; this call
+ * synchronises the device, prints the per-kernel totals to stdout and clears the trace.  No-op otherwise. */
+int clipk_trace_dump(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Engine building block (also the unit-test entry of the tcgen05 pipeline):

@@ -93,6 +93,24 @@ if __name__ == "__main__":
         gemm(1024, 512, 768, nb=64)
         gemm(1024, 1024, 768, nb=32)
         gemm(2048, 2048, 768, nb=4)
+    if cmd == "epi":
+        gemm(1024, 576, 64, nb=256)
+        gemm(1024, 576, 128, nb=256)
+        gemm(1024, 576, 384, nb=256)
+        gemm(1024, 576, 768, nb=256)
+        gemm(1024, 768, 64, nb=256)
+        gemm(1024, 768, 576, nb=256)
+    if cmd == "bn":
+        gemm(4096, 256, 4096, nb=16)
+        gemm(4096, 192, 4096, nb=16)
+        gemm(4096, 128, 4096, nb=32)
+        gemm(4096, 64, 4096, nb=64)
+    if cmd == "trace":      # run with CLIPK_TRACE=1
+        B, grp = int(sys.argv[2]), int(sys.argv[3])
+        allpairs_once(B, 576, 768, grp)
+        _lib.lib().clipk_trace_dump()
+        allpairs_once(B, 576, 768, grp)
+        _lib.lib().clipk_trace_dump()
     if cmd == "fwdonce":
         V = torch.randn(int(sys.argv[2]), 576, 768, device="cuda").to(torch.bfloat16)
         T = torch.randn(1024, 768, device="cuda").to(torch.bfloat16)
