@@ -85,8 +85,18 @@ struct Store {
     } else {
       float* dst = reinterpret_cast<float*>(p.C) + b * p.strideC + (int64_t)m * p.ldc + n;
       if (p.accumulate) {
-        for (int j = 0; j < 32; ++j)
-          if (j < valid) dst[j] += v[j];
+        if (valid >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          float4 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = d4[j];            // all loads in flight before the first store
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(o[j].x + v[4 * j], o[j].y + v[4 * j + 1], o[j].z + v[4 * j + 2], o[j].w + v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (j < valid) dst[j] += v[j];
+        }
       } else {
         store_f32x32(dst, v, valid);
       }

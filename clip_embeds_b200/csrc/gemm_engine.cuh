@@ -253,7 +253,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = ptx::umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -265,6 +265,11 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
         ptx::mbar_wait(&tempty_bar[buf], bphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kAccCols;
+        // N tail: the last n-tile only multiplies the columns that exist (rounded up to the MMA granularity of 16)
+        const int n0t = ((tile - bl0 * tiles_per_batch) % pb.tiles_n) * BN;
+        const int nrem = pb.N - n0t;
+        const uint32_t idesc = nrem >= BN ? idesc_full
+                                          : ptx::umma_idesc_bf16(BM, (nrem + 15) & ~15, A_MN ? 1 : 0, B_MN ? 1 : 0);
         uint32_t accum = 0;
         for (int q = 0; q < pb.num_pairs; ++q) {
           const int nks = ksteps_of(pb, q, b);
@@ -313,8 +318,11 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       const int m = m0 + q4 * 32 + lane;
       epi.tile_begin(b, m, n0);
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * kAccCols;
+      // 64-column slabs that hold at least one existing output column (the MMA warp skips the rest of an N tail)
+      const int jn = (pb.N - n0 + 63) >> 6;
+      const int jmax = jn < BN / 64 ? jn : BN / 64;
 #pragma unroll 1
-      for (int j = 0; j < BN / 64; ++j) {
+      for (int j = 0; j < jmax; ++j) {
         const int c = 2 * j + half;
         float v[32];
         ptx::tmem_ld_32x32(tacc + c * 32, v);
@@ -322,7 +330,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
           float v1[32];
           ptx::tmem_ld_32x32(tacc + BN + c * 32, v1);
           ptx::tmem_ld_wait();
-          if (j == BN / 64 - 1) {                  // accumulator drained: hand the TMEM buffer back to the MMA warp
+          if (j == jmax - 1) {                  // accumulator drained: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
@@ -330,7 +338,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
           epi.chunk2(b, m, n0 + c * 32, v, v1);
         } else {
           ptx::tmem_ld_wait();
-          if (j == BN / 64 - 1) {
+          if (j == jmax - 1) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);

@@ -100,6 +100,12 @@ if __name__ == "__main__":
         gemm(1024, 576, 768, nb=256)
         gemm(1024, 768, 64, nb=256)
         gemm(1024, 768, 576, nb=256)
+    if cmd == "k5":
+        gemm(1024, 768, 576, nb=128, b_mn=1)
+        gemm(1024, 768, 12672, nb=6, b_mn=1)
+        gemm(1024, 768, 12672, nb=6, b_mn=0)
+        gemm(1024, 768, 6336, nb=12, b_mn=1)
+        gemm(1024, 768, 3168, nb=24, b_mn=1)
     if cmd == "bn":
         gemm(4096, 256, 4096, nb=16)
         gemm(4096, 192, 4096, nb=16)
