@@ -114,6 +114,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
                    uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows) {
+  return make_tmap_bf16_box(out, base, inner, rows, batch, row_stride_bytes, batch_stride_bytes, 64, box_rows);
+}
+
+int make_tmap_bf16_box(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
   auto encode = get_encode_fn();
   if (encode == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -130,10 +135,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
   if (batch == 1 || batch_stride_bytes == 0) batch_stride_bytes = row_stride_bytes * (rows > 0 ? rows : 1);
   cuuint64_t dims[3] = {inner, rows, batch};
   cuuint64_t strides[2] = {row_stride_bytes, batch_stride_bytes};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  // the swizzle span equals the box's inner extent in bytes: 64 elements -> 128 B, 32 elements -> 64 B
+  const CUtensorMapSwizzle swz = box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): dims (%llu,%llu,%llu) strides (%llu,%llu) box rows %u", (int)r,

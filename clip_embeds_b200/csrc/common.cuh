@@ -11,6 +11,7 @@
 
 #include "../../include/clipk.h"
 #include "gemm_engine.cuh"
+#include "gemm2_engine.cuh"
 
 namespace clipk {
 
@@ -50,6 +51,10 @@ void trace_end(cudaStream_t st);                    // bump the library-wide ker
 //   strides = byte strides of dims 1 and 2 (multiples of 16)
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
                    uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_rows);
+
+// same with an explicit inner box extent: 64 elements (SWIZZLE_128B) or 32 elements (SWIZZLE_64B)
+int make_tmap_bf16_box(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                       uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_inner, uint32_t box_rows);
 
 struct OperandDesc {
   const void* ptr = nullptr;
@@ -124,6 +129,73 @@ int launch_gemm(const OperandDesc* a, const OperandDesc* b, int num_pairs, const
   const bool tr = trace_enabled();
   if (tr) trace_begin(__PRETTY_FUNCTION__, stream);
   kern<<<grid, eng::kThreads, L::kTotal, stream>>>(maps, pb, ep);
+  if (tr) trace_end(stream);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// CTA-pair engine (gemm2_engine.cuh): same operand / epilogue description as launch_gemm; a cluster of two CTAs
+// computes one 256 x BN tile (each CTA: 128 rows of A, BN/2 rows of B).
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, const int* ksteps, const int* ksub,
+                 int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t stream) {
+  constexpr bool kDual = eng::epi_dual<Epi>::value;
+  constexpr bool kTmaOut = eng::epi_tma_out<Epi>::value;
+  using L = eng2::SmemLayout<BN, kDual, kTmaOut>;
+  eng::OperandMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  eng::Problem pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.M = M;
+  pb.N = N;
+  pb.batches = batches;
+  pb.tiles_m = (M + 2 * eng2::BM - 1) / (2 * eng2::BM);
+  pb.tiles_n = (N + BN - 1) / BN;
+  pb.num_pairs = num_pairs;
+  pb.reverse = a[0].reverse;
+  for (int q = 0; q < num_pairs; ++q) {
+    pb.ksteps[q] = ksteps[q];
+    pb.ksub[q] = ksub[q] > 0 ? ksub[q] : (ksteps[q] > 0 ? ksteps[q] : 1);
+    pb.a_bmul[q] = a[q].bmul; pb.a_smul[q] = a[q].smul;
+    pb.b_bmul[q] = b[q].bmul; pb.b_smul[q] = b[q].smul;
+    pb.sub_per_batch[q] = a[q].sub_per_batch;
+    pb.sub_total[q] = a[q].sub_total;
+    if (!A_MN) {
+      CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].k, a[q].rows, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, eng2::BM));
+    } else {
+      CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].rows, a[q].k, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, 64));
+    }
+    if (!B_MN) {
+      CLIPK_TRY(make_tmap_bf16(&maps.b[q], b[q].ptr, b[q].k, b[q].rows, b[q].batch, b[q].ld * 2, b[q].batch_stride * 2, BN / 2));
+    } else {
+      CLIPK_TRY(make_tmap_bf16(&maps.b[q], b[q].ptr, b[q].rows, b[q].k, b[q].batch, b[q].ld * 2, b[q].batch_stride * 2, 64));
+    }
+  }
+  if constexpr (kDual) {
+    pb.a_bmul[1] = a[1].bmul;
+    CLIPK_TRY(make_tmap_bf16(&maps.a[1], a[1].ptr, a[1].k, a[1].rows, a[1].batch, a[1].ld * 2, a[1].batch_stride * 2, eng2::BM));
+  }
+  if constexpr (kTmaOut) {
+    const eng::OutDesc& o = ep.out;
+    CLIPK_TRY(make_tmap_bf16_box(&maps.out, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, (uint64_t)o.batches,
+                                 (uint64_t)o.ld * 2, (uint64_t)o.stride * 2, 32, 32));   // one [32 x 32] box per epilogue warp
+  }
+  const int total = pb.batches * pb.tiles_m * pb.tiles_n;
+  if (total <= 0) return 0;
+  auto kern = eng2::gemm2_kernel<BN, A_MN, B_MN, Epi>;
+  static std::atomic<uint64_t> attr_mask{0};
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (total < pairs ? total : pairs);
+  const bool tr = trace_enabled();
+  if (tr) trace_begin(__PRETTY_FUNCTION__, stream);
+  kern<<<grid, eng2::kThreads, L::kTotal, stream>>>(maps, pb, ep);
   if (tr) trace_end(stream);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());

@@ -203,8 +203,15 @@ struct StoreTma {
 // acc[m=text k][n=patch p] = <T_k, V_ip> (raw).  s = acc * rnT[k] * rnV[i,p];  a = sigmoid(10 s)  (pacl.py:133)
 // output (TMA store): A bf16 [batch][M][Ppad], zero in the pad columns;
 // side output: num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
+// Side data: lane l holds rnV[i, n + l] of the chunk (one coalesced load issued a chunk ahead, broadcast by shuffle).
+__device__ __forceinline__ void bf16_round_pair(float& a0, float& a1) {
+  const uint32_t pk = ptx::pack_bf16x2(a0, a1);       // one cvt.rn.bf16x2 for two values
+  a0 = __uint_as_float(pk << 16);
+  a1 = __uint_as_float(pk & 0xFFFF0000u);
+}
 struct PaclAct {
   static constexpr bool kTmaOut = true;
+  using Side = float;
   struct Params {
     eng::OutDesc out;   // A
     const float* rnV;   // [batch][P]
@@ -220,21 +227,38 @@ struct PaclAct {
     rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
     rt5 = 5.f * rt;
   }
-  __device__ void chunk(int b, int, int n, float* v) {
+  __device__ Side pre(int b, int, int n) const {
     const int lane = (int)ptx::lane_id();
-    // one coalesced load of the 32 patch norms of this chunk, broadcast by shuffle (branch-free inner loop)
-    const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
-    const bool ones = p.act == CLIPK_ACT_ONES;
+    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+  }
+  __device__ void chunk(int, int, int n, float* v, const Side& rn_l) {
+    if (p.act == CLIPK_ACT_ONES) {                 // warp-uniform
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float rnj = __shfl_sync(0xffffffffu, rn_l, j);
-      const float x = v[j] * rnj;                  // <T_k, V_p> / |V_p|   (score = x * rnT)
-      float t;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * rt5));
-      float a = ones ? 1.f : bf16_round(fmaf(0.5f, t, 0.5f));
-      a = (n + j < p.P) ? a : 0.f;
-      acc = fmaf(a, v[j], acc);                    // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
-      v[j] = a;
+      for (int j = 0; j < 32; ++j) {
+        acc += v[j];
+        v[j] = 1.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float r0 = __shfl_sync(0xffffffffu, rn_l, j);      // rnV of column j (per column; rt5 is per row)
+        const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v[j] * rt5 * r0));       // sigmoid(10 s) = 0.5 tanh(5 s) + 0.5
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v[j + 1] * rt5 * r1));
+        float a0 = fmaf(0.5f, t0, 0.5f);
+        float a1 = fmaf(0.5f, t1, 0.5f);
+        bf16_round_pair(a0, a1);                   // the value the pooling GEMM will see
+        acc = fmaf(a0, v[j], acc);                 // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
+        acc = fmaf(a1, v[j + 1], acc);
+        v[j] = a0;
+        v[j + 1] = a1;
+      }
+    }
+    if (n + 32 > p.P) {                            // chunk straddles the end of the patch axis: zero the pad columns
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j >= p.P) v[j] = 0.f;              // (their acc contribution is already 0: TMA zero-fills V rows >= P)
     }
   }
   __device__ void tile_end(int b, int m, int, int, int) {
@@ -295,6 +319,7 @@ struct GNeg {
 struct DsDual {
   static constexpr bool kTmaOut = true;
   static constexpr bool kDual = true;
+  using Side = float;          // lane l holds rnV[i, n + l]
   struct Params {
     eng::OutDesc out;        // E [batch][M][Ppad]
     const float* rnV;        // [batch][P]
@@ -310,25 +335,38 @@ struct DsDual {
     rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
     al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f;
   }
-  __device__ void chunk2(int b, int m, int n, float* x, float* d) {
+  __device__ Side pre(int b, int, int n) const {
     const int lane = (int)ptx::lane_id();
-    const float rn_l = (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+  }
+  __device__ void chunk2(int b, int m, int n, float* x, float* d, const Side& rn_l) {
+    const int lane = (int)ptx::lane_id();
     const bool ones = p.act == CLIPK_ACT_ONES;
     const float gate = (m < p.M && !ones) ? 10.f : 0.f;
     const float art = al * rt;
     const float rt5 = 5.f * rt;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float rnj = __shfl_sync(0xffffffffu, rn_l, j);      // 0 for p >= P: masks the pad columns
-      const float xs = x[j] * rnj;
-      float t;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xs * rt5));
-      const float a = ones ? 1.f : bf16_round(fmaf(0.5f, t, 0.5f));
-      const float da = fmaf(art, x[j], d[j]);
-      const float ds = da * gate * a * (1.f - a);
-      const float dsv = ds * rnj;
-      x[j] = (n + j < p.P) ? fmaf(al, a, dsv) : 0.f;            // E
-      d[j] = ds * xs * rt;                                       // ds * s  (0 in pad columns / invalid rows)
+    for (int j = 0; j < 32; j += 2) {
+      const float r0 = __shfl_sync(0xffffffffu, rn_l, j);        // 0 for p >= P: masks the pad columns
+      const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+      const float xs0 = x[j] * r0, xs1 = x[j + 1] * r1;
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(xs0 * rt5));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(xs1 * rt5));
+      float a0 = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
+      float a1 = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
+      bf16_round_pair(a0, a1);
+      const float ds0 = fmaf(art, x[j], d[j]) * gate * a0 * (1.f - a0);
+      const float ds1 = fmaf(art, x[j + 1], d[j + 1]) * gate * a1 * (1.f - a1);
+      x[j] = fmaf(al, a0, ds0 * r0);                              // E
+      x[j + 1] = fmaf(al, a1, ds1 * r1);
+      d[j] = ds0 * xs0 * rt;                                      // ds * s  (0 in pad columns / invalid rows)
+      d[j + 1] = ds1 * xs1 * rt;
+    }
+    if (n + 32 > p.P) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j >= p.P) x[j] = 0.f;
     }
     const float cs = ptx::warp_colsum32(d);   // lane j: sum over this warp's 32 rows of column n + j
     const int col = n + lane;
@@ -341,9 +379,12 @@ struct DsDual {
 // acc[m=patch p][n=d] = sum_k a_ikp Gn_ik[d] + sum_k E_ikp T^_k[d];  dV_ip = acc - rnV_ip^2 dsdot_ip V_ip  (TMA store)
 struct DvOut {
   static constexpr bool kTmaOut = true;
+  struct Side {
+    uint4 q[4];     // 32 bf16 of V[b][m][n .. n+32)
+  };
   struct Params {
     eng::OutDesc out;         // dV [batch][M][N]
-    const __nv_bfloat16* V;   // [batch][M][N]
+    const __nv_bfloat16* V;   // [batch][M][N]   (N % 8 == 0: 16-byte aligned rows)
     const float* rnV;         // [batch][M]
     const float* dsdot;       // [batch][M]
     int M, N;
@@ -352,19 +393,31 @@ struct DvOut {
   float coef;
   __device__ explicit DvOut(const Params& pp) : p(pp), coef(0.f) {}
   __device__ void tile_begin(int b, int m, int) {
+    coef = 0.f;
     if (m < p.M) {
       const float r = __ldg(p.rnV + (int64_t)b * p.M + m);
       coef = r * r * __ldg(p.dsdot + (int64_t)b * p.M + m);
     }
   }
-  __device__ void chunk(int b, int m, int n, float* v) {
-    if (m >= p.M || n >= p.N) return;
-    const int valid = min(32, p.N - n);
-    const int64_t off = ((int64_t)b * p.M + m) * p.N + n;
-    float x[32];
-    load_bf16x32(p.V + off, x, valid);
+  __device__ Side pre(int b, int m, int n) const {
+    Side s;
+    const uint4* src = reinterpret_cast<const uint4*>(p.V + ((int64_t)b * p.M + m) * p.N + n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaf(-coef, x[j], v[j]);
+    for (int j = 0; j < 4; ++j)
+      s.q[j] = (m < p.M && n + 8 * j + 8 <= p.N) ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
+    return s;
+  }
+  __device__ void chunk(int, int, int, float* v, const Side& s) {
+    const float nc = -coef;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w[4] = {s.q[j].x, s.q[j].y, s.q[j].z, s.q[j].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        v[8 * j + 2 * t] = fmaf(nc, __uint_as_float(w[t] << 16), v[8 * j + 2 * t]);
+        v[8 * j + 2 * t + 1] = fmaf(nc, __uint_as_float(w[t] & 0xFFFF0000u), v[8 * j + 2 * t + 1]);
+      }
+    }
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };

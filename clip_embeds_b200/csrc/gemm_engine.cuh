@@ -39,6 +39,17 @@ struct epi_dual : std::false_type {};
 template <class E>
 struct epi_dual<E, std::void_t<decltype(E::kDual)>> : std::bool_constant<E::kDual> {};
 
+// Epi::Side (optional): per-chunk side data that `Side pre(b, m, n)` loads ahead of time and chunk() consumes
+template <class E, class = void>
+struct epi_has_side : std::false_type {};
+template <class E>
+struct epi_has_side<E, std::void_t<typename E::Side>> : std::true_type {};
+struct NoSide {};
+template <class E, class = void>
+struct side_of { using type = NoSide; };
+template <class E>
+struct side_of<E, std::void_t<typename E::Side>> { using type = typename E::Side; };
+
 // description of the TMA-stored output (member `out` of Epi::Params when Epi::kTmaOut)
 struct OutDesc {
   void* ptr;
@@ -326,6 +337,8 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
         const int c = 2 * j + half;
         float v[32];
         ptx::tmem_ld_32x32(tacc + c * 32, v);
+        [[maybe_unused]] typename side_of<Epi>::type side{};
+        if constexpr (epi_has_side<Epi>::value) side = epi.pre(b, m, n0 + c * 32);
         if constexpr (DUAL) {
           float v1[32];
           ptx::tmem_ld_32x32(tacc + BN + c * 32, v1);
@@ -335,7 +348,8 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
           }
-          epi.chunk2(b, m, n0 + c * 32, v, v1);
+          if constexpr (epi_has_side<Epi>::value) epi.chunk2(b, m, n0 + c * 32, v, v1, side);
+          else epi.chunk2(b, m, n0 + c * 32, v, v1);
         } else {
           ptx::tmem_ld_wait();
           if (j == jmax - 1) {
@@ -343,7 +357,8 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
           }
-          epi.chunk(b, m, n0 + c * 32, v);
+          if constexpr (epi_has_side<Epi>::value) epi.chunk(b, m, n0 + c * 32, v, side);
+          else epi.chunk(b, m, n0 + c * 32, v);
         }
         if constexpr (TMA_OUT) {
           uint8_t* sbuf = out_smem + (slab & 1) * L::kOutSlabBytes;

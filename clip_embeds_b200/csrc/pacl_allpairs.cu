@@ -20,6 +20,8 @@
 //             K6  dV_i = A^T Gn + E^T T^ - rnV^2 dsdot V      (two operand pairs, epilogue DvOut, TMA store)
 //  with G_ik = alpha_ik t^_k - beta_ik u_ik the gradient w.r.t. the pooled vector, E = ds rnV + alpha a and
 //  T^ = bf16(T rnT): sum_k a G = E-part + A^T Gn because alpha a t^ is already inside E^T T^.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_util.cuh"
@@ -173,6 +175,26 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
   return off;
 }
 
+// Engine choice per kernel: bit i of CLIPK_AP_ENGINE2 selects the CTA-pair engine for kernel i
+// (0: K1 activations, 1: K2 pooling, 2: K4 dS/E, 3: K5 dT, 4: K6 dV).  Default: all on the CTA-pair engine.
+static int engine2_mask() {
+  static const int m = [] {
+    const char* e = getenv("CLIPK_AP_ENGINE2");
+    return e != nullptr ? atoi(e) : 0x1F;
+  }();
+  return m;
+}
+enum { kK1 = 1, kK2 = 2, kK4 = 4, kK5 = 8, kK6 = 16 };
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+static int gemm_on(bool pair, const OperandDesc* a, const OperandDesc* b, int npairs, const int* ks, const int* ksub,
+                   int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t st) {
+  if constexpr (!B_MN || BN % 128 == 0) {
+    if (pair && M > eng::BM) return launch_gemm2<BN, A_MN, B_MN, Epi>(a, b, npairs, ks, ksub, M, N, batches, ep, st);
+  }
+  return launch_gemm<BN, A_MN, B_MN, Epi>(a, b, npairs, ks, ksub, M, N, batches, ep, st);
+}
+
 static int pick_bn(int n) {
   // largest tile whose padding waste stays under ~12%, else the waste-free 64-multiple
   const int cands[3] = {256, 192, 128};
@@ -192,11 +214,12 @@ static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, in
   b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
   const int ks[1] = {(D + 63) / 64};
   epi::PaclAct::Params ep{{w.A, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, num0, Bt, P, Ppad, act};
+  const bool pair = (engine2_mask() & kK1) != 0;
   switch (pick_bn(Ppad)) {
-    case 256: return launch_gemm<256, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 192: return launch_gemm<192, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    case 128: return launch_gemm<128, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
-    default: return launch_gemm<64, false, false, epi::PaclAct>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 256: return gemm_on<256, false, false, epi::PaclAct>(pair, &a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 192: return gemm_on<192, false, false, epi::PaclAct>(pair, &a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    case 128: return gemm_on<128, false, false, epi::PaclAct>(pair, &a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
+    default: return gemm_on<64, false, false, epi::PaclAct>(pair, &a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
   }
 }
 
@@ -210,14 +233,14 @@ static void k2_operands(const ApWorkspace& w, const __nv_bfloat16* V0, int gi, i
 }
 
 template <class Epi, bool A_MN>
-static int launch_nd(const OperandDesc* a, const OperandDesc* b, int npairs, const int* ks, const int* ksub, int M,
-                     int D, int batches, const typename Epi::Params& ep, cudaStream_t st) {
+static int launch_nd(bool pair, const OperandDesc* a, const OperandDesc* b, int npairs, const int* ks, const int* ksub,
+                     int M, int D, int batches, const typename Epi::Params& ep, cudaStream_t st) {
   // N = D output columns, B operand MN-major (d contiguous)
   switch (pick_bn(D)) {
-    case 256: return launch_gemm<256, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
-    case 192: return launch_gemm<192, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
-    case 128: return launch_gemm<128, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
-    default: return launch_gemm<64, A_MN, true, Epi>(a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    case 256: return gemm_on<256, A_MN, true, Epi>(pair, a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    case 192: return gemm_on<192, A_MN, true, Epi>(pair, a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    case 128: return gemm_on<128, A_MN, true, Epi>(pair, a, b, npairs, ks, ksub, M, D, batches, ep, st);
+    default: return gemm_on<64, A_MN, true, Epi>(pair, a, b, npairs, ks, ksub, M, D, batches, ep, st);
   }
 }
 
@@ -273,7 +296,7 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     k2_operands(w[l], V0, gi, Bt, P, D, &a, &b);
     const int ks[1] = {Ppad / 64};
     epi::Usq::Params ep{usq + (int64_t)i0 * Bt, Bt, D};
-    CLIPK_TRY(launch_nd<epi::Usq, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+    CLIPK_TRY(launch_nd<epi::Usq, false>((engine2_mask() & kK2) != 0, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
   }
   if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
   const int64_t n = (int64_t)Bi * Bt;
@@ -324,7 +347,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       k2_operands(w, V0, gi, Bt, P, D, &a, &b);
       const int ks[1] = {Ppad / 64};
       epi::GNeg::Params ep{{w.G, D, (int64_t)Bt * D, Bt, D, gi}, beta0, Bt};
-      CLIPK_TRY(launch_nd<epi::GNeg, false>(&a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+      CLIPK_TRY(launch_nd<epi::GNeg, false>((engine2_mask() & kK2) != 0, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
     }
     // K4 (dual): x = T V^T (recomputed), d = Gn V^T  ->  E, dsdot
     {
@@ -335,9 +358,9 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       const int ks[1] = {(D + 63) / 64};
       epi::DsDual::Params ep{{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, alpha0, dsdot0, Bt, P, Ppad, act};
       if (Ppad % 128 == 0 || Ppad > 64) {
-        CLIPK_TRY(launch_gemm<128, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls));
+        CLIPK_TRY((gemm_on<128, false, false, epi::DsDual>((engine2_mask() & kK4) != 0, a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
       } else {
-        CLIPK_TRY(launch_gemm<64, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls));
+        CLIPK_TRY((gemm_on<64, false, false, epi::DsDual>((engine2_mask() & kK4) != 0, a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
       }
     }
     // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch; split-K over images so that
@@ -355,7 +378,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       const int ks[1] = {spb * (Ppad / 64)};
       const int ksub[1] = {Ppad / 64};
       epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
-      CLIPK_TRY(launch_nd<epi::Store<false>, false>(&a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
+      CLIPK_TRY(launch_nd<epi::Store<false>, false>((engine2_mask() & kK5) != 0, &a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
     }
     // K6: dV_i = A_i^T Gn_i + E_i^T T^ - rnV^2 dsdot V
     {
@@ -369,7 +392,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       b[1].ptr = sh.That; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
       const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
       epi::DvOut::Params ep{{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi}, V0, rnV0, dsdot0, P, D};
-      CLIPK_TRY(launch_nd<epi::DvOut, true>(a, b, 2, ks, ks, P, D, gi, ep, ls));
+      CLIPK_TRY(launch_nd<epi::DvOut, true>((engine2_mask() & kK6) != 0, a, b, 2, ks, ks, P, D, gi, ep, ls));
     }
   }
   if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
