@@ -142,7 +142,9 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
                  int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t stream) {
   constexpr bool kDual = eng::epi_dual<Epi>::value;
   constexpr bool kTmaOut = eng::epi_tma_out<Epi>::value;
-  using L = eng2::SmemLayout<BN, kDual, kTmaOut>;
+  constexpr bool kTmaOut2 = eng::epi_tma_out2<Epi>::value;
+  constexpr bool kChunkIn = eng::epi_chunk_in<Epi>::value;
+  using L = eng2::SmemLayout<BN, kDual, kTmaOut, kTmaOut2, kChunkIn>;
   eng::OperandMaps maps;
   memset(&maps, 0, sizeof(maps));
   eng::Problem pb;
@@ -180,6 +182,16 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
     const eng::OutDesc& o = ep.out;
     CLIPK_TRY(make_tmap_bf16_box(&maps.out, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, (uint64_t)o.batches,
                                  (uint64_t)o.ld * 2, (uint64_t)o.stride * 2, 32, 32));   // one [32 x 32] box per epilogue warp
+  }
+  if constexpr (kTmaOut2) {
+    const eng::OutDesc& o = ep.out2;
+    CLIPK_TRY(make_tmap_bf16_box(&maps.out2, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, (uint64_t)o.batches,
+                                 (uint64_t)o.ld * 2, (uint64_t)o.stride * 2, 32, 32));
+  }
+  if constexpr (kChunkIn) {
+    const eng::OutDesc& o = ep.in;
+    CLIPK_TRY(make_tmap_bf16_box(&maps.in, o.ptr, (uint64_t)o.cols, (uint64_t)o.rows, (uint64_t)o.batches,
+                                 (uint64_t)o.ld * 2, (uint64_t)o.stride * 2, 32, 32));
   }
   const int total = pb.batches * pb.tiles_m * pb.tiles_n;
   if (total <= 0) return 0;

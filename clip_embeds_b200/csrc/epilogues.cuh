@@ -375,6 +375,118 @@ struct DsDual {
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1 (bwd)
+// The backward's recompute of GEMM1 (CTA-pair engine): besides the activations A it stores the text-normalised raw
+// scores  X = bf16(<t^_k, V_ip>) = bf16(acc * rnT[k]),  which the dS kernel (DsIn) reads back chunk by chunk through
+// TMA instead of recomputing the T V^T GEMM a second time.
+struct PaclActS {
+  static constexpr bool kTmaOut = true;
+  static constexpr bool kTmaOut2 = true;
+  using Side = float;          // lane l holds rnV[i, n + l]
+  struct Params {
+    eng::OutDesc out;    // A [batch][M][Ppad]
+    eng::OutDesc out2;   // X [batch][M][Ppad]
+    const float* rnV;    // [batch][P]
+    const float* rnT;    // [M]
+    int M, P, Ppad, act;
+  };
+  Params p;
+  float rt, rt5;
+  __device__ explicit PaclActS(const Params& pp) : p(pp), rt(0.f), rt5(0.f) {}
+  __device__ void tile_begin(int, int m, int) {
+    rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
+    rt5 = 5.f * rt;
+  }
+  __device__ Side pre(int b, int, int n) const {
+    const int lane = (int)ptx::lane_id();
+    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+  }
+  __device__ void chunk(int, int, int n, float* v, const Side& rn_l, const uint32_t*, float* x) {
+    const bool ones = p.act == CLIPK_ACT_ONES;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float r0 = __shfl_sync(0xffffffffu, rn_l, j);
+      const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+      x[j] = v[j] * rt;                                    // pad columns: V rows >= P are zero-filled -> 0
+      x[j + 1] = v[j + 1] * rt;
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v[j] * rt5 * r0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v[j + 1] * rt5 * r1));
+      v[j] = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
+      v[j + 1] = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
+    }
+    if (n + 32 > p.P) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j >= p.P) v[j] = 0.f;
+    }
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM3 (bwd)
+// acc[m=text k][n=patch p] = d = <Gn_ik, V_ip>;  input chunk X = <t^_k, V_ip> (bf16, written by PaclActS).
+//   s  = X rnV,  a = bf16(sigmoid(10 s))
+//   da = alpha_ik X + d   ( = <G_ik, V_ip>,  G = alpha t^ - beta u ),   ds = da * 10 a (1 - a)
+//   E[i,k,p] = ds * rnV[i,p] + alpha_ik a     (TMA store; operand of dt^ += E V  and of dV += E^T T^)
+//   dsdot[i,p] += sum_k ds * s                (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
+struct DsIn {
+  static constexpr bool kTmaOut = true;
+  static constexpr bool kChunkIn = true;
+  using Side = float;          // lane l holds rnV[i, n + l]
+  struct Params {
+    eng::OutDesc out;        // E [batch][M][Ppad]
+    eng::OutDesc in;         // X [batch][M][Ppad]
+    const float* rnV;        // [batch][P]
+    const float* alpha;      // [batch][M]
+    float* dsdot;            // [batch][P]
+    int M, P, Ppad, act;
+  };
+  Params p;
+  float al;
+  __device__ explicit DsIn(const Params& pp) : p(pp), al(0.f) {}
+  __device__ void tile_begin(int b, int m, int) { al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f; }
+  __device__ Side pre(int b, int, int n) const {
+    const int lane = (int)ptx::lane_id();
+    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+  }
+  __device__ void chunk(int b, int m, int n, float* d, const Side& rn_l, const uint32_t* in, float*) {
+    const int lane = (int)ptx::lane_id();
+    const bool ones = p.act == CLIPK_ACT_ONES;
+    const float gate = (m < p.M && !ones) ? 10.f : 0.f;
+    float dss[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float r0 = __shfl_sync(0xffffffffu, rn_l, j);        // 0 for p >= P: masks the pad columns
+      const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+      const float x0 = __uint_as_float(in[j >> 1] << 16);
+      const float x1 = __uint_as_float(in[j >> 1] & 0xFFFF0000u);
+      const float s0 = x0 * r0, s1 = x1 * r1;
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(5.f * s0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(5.f * s1));
+      float a0 = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
+      float a1 = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
+      bf16_round_pair(a0, a1);
+      const float ds0 = fmaf(al, x0, d[j]) * gate * a0 * (1.f - a0);
+      const float ds1 = fmaf(al, x1, d[j + 1]) * gate * a1 * (1.f - a1);
+      d[j] = fmaf(al, a0, ds0 * r0);                              // E
+      d[j + 1] = fmaf(al, a1, ds1 * r1);
+      dss[j] = ds0 * s0;                                          // ds * s  (0 in pad columns / invalid rows)
+      dss[j + 1] = ds1 * s1;
+    }
+    if (n + 32 > p.P) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j >= p.P) d[j] = 0.f;
+    }
+    const float cs = ptx::warp_colsum32(dss);   // lane j: sum over this warp's 32 rows of column n + j
+    const int col = n + lane;
+    if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
 // ------------------------------------------------------------------------------------ PACL all-pairs, dV (bwd)
 // acc[m=patch p][n=d] = sum_k a_ikp Gn_ik[d] + sum_k E_ikp T^_k[d];  dV_ip = acc - rnV_ip^2 dsdot_ip V_ip  (TMA store)
 struct DvOut {

@@ -45,14 +45,17 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiBarId = 1;
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN, bool DUAL = false, bool TMA_OUT = false>
+template <int BN, bool DUAL = false, bool TMA_OUT = false, bool TMA_OUT2 = false, bool CHUNK_IN = false>
 struct SmemLayout {
   static constexpr int kA1Bytes = BM * BK * 2;
   static constexpr int kABytes = kA1Bytes * (DUAL ? 2 : 1);
   static constexpr int kBBytes = (BN / 2) * BK * 2;               // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutChunkBytes = 32 * 64;                  // one epilogue warp's [32 rows][32 bf16] chunk
-  static constexpr int kOutBytes = TMA_OUT ? kEpiWarps * 2 * kOutChunkBytes : 0;   // double-buffered per warp
+  static constexpr int kOut1Bytes = TMA_OUT ? kEpiWarps * 2 * kOutChunkBytes : 0;  // double-buffered per warp
+  static constexpr int kOut2Bytes = TMA_OUT2 ? kEpiWarps * 2 * kOutChunkBytes : 0;
+  static constexpr int kInBytes = CHUNK_IN ? kEpiWarps * 2 * kOutChunkBytes : 0;
+  static constexpr int kOutBytes = kOut1Bytes + kOut2Bytes + kInBytes;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kAvail = kSmemBudget - 1024 /*align slack*/ - kBarrierBytes - kOutBytes;
   static constexpr int kStagesRaw = kAvail / kStageBytes;
@@ -95,11 +98,15 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   constexpr bool DUAL = epi_dual<Epi>::value;
   constexpr bool TMA_OUT = epi_tma_out<Epi>::value;
   constexpr bool HAS_SIDE = epi_has_side<Epi>::value;
+  constexpr bool TMA_OUT2 = eng::epi_tma_out2<Epi>::value;
+  constexpr bool CHUNK_IN = eng::epi_chunk_in<Epi>::value;
+  static_assert(!TMA_OUT2 || TMA_OUT, "a second output needs the first");
+  static_assert(!(TMA_OUT2 || CHUNK_IN) || (HAS_SIDE && !DUAL), "chunk-in / second output: uniform functors only");
   static_assert(BN % 32 == 0 && BN <= 256, "BN: multiple of 32, at most 256");
   static_assert(!B_MN || (BN % 128 == 0), "MN-major B: each CTA's half must be whole 64-wide swizzle groups");
   static_assert(!DUAL || (BN <= 128 && !A_MN), "dual accumulators: BN <= 128, K-major A operands");
   constexpr int kAccCols = DUAL ? 2 * BN : BN;
-  using L = SmemLayout<BN, DUAL, TMA_OUT>;
+  using L = SmemLayout<BN, DUAL, TMA_OUT, TMA_OUT2, CHUNK_IN>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,6 +116,9 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   uint64_t* tfull_bar = empty_bar + kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]  (the leader's copy is the live one)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* in_bar = tempty_bar + 4;           // [kEpiWarps][2]  per-warp "input chunk landed" barriers (kChunkIn)
+  uint8_t* out2_smem = out_smem + L::kOut1Bytes;
+  uint8_t* in_smem = out2_smem + L::kOut2Bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,6 +136,8 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
     }
     if constexpr (DUAL) ptx::prefetch_tmap(&maps.a[1]);
     if constexpr (TMA_OUT) ptx::prefetch_tmap(&maps.out);
+    if constexpr (TMA_OUT2) ptx::prefetch_tmap(&maps.out2);
+    if constexpr (CHUNK_IN) ptx::prefetch_tmap(&maps.in);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -135,6 +147,9 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 2 * kEpiWarps);   // every epilogue warp of both CTAs
+    }
+    if constexpr (CHUNK_IN) {
+      for (int i = 0; i < 2 * kEpiWarps; ++i) ptx::mbar_init(&in_bar[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -248,8 +263,20 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
 #endif
     TileCoord tc = tile_coord<BN>(pb, cluster_id, total_tiles, tiles_per_batch, rank);
     [[maybe_unused]] typename eng::side_of<Epi>::type side{};
-    if constexpr (HAS_SIDE) {
-      if (tc.valid) side = epi.pre(tc.b, tc.m0 + q4 * 32 + lane, tc.n0 + half * 32);
+    const int ew = warp - kEpiWarp0;
+    // kChunkIn: TMA-load this warp's [32 x 32] bf16 box of the input tensor for chunk number `g` into buffer g & 1
+    auto issue_in = [&](int g, int bb, int mrow0, int ncol) {
+      if constexpr (CHUNK_IN) {
+        if (lane == 0) {
+          uint64_t* bar = &in_bar[ew * 2 + (g & 1)];
+          ptx::mbar_arrive_expect_tx(bar, L::kOutChunkBytes);
+          ptx::tma_load_3d(in_smem + (ew * 2 + (g & 1)) * L::kOutChunkBytes, &maps.in, bar, ncol, mrow0, bb);
+        }
+      }
+    };
+    if (tc.valid) {
+      if constexpr (HAS_SIDE) side = epi.pre(tc.b, tc.m0 + q4 * 32 + lane, tc.n0 + half * 32);
+      issue_in(0, tc.b, tc.m0 + q4 * 32, tc.n0 + half * 32);
     }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const TileCoord nx = tile_coord<BN>(pb, tile + num_clusters, total_tiles, tiles_per_batch, rank);
@@ -268,11 +295,15 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
       const int jn = (pb.N - n0 + 63) >> 6;
       const int jmax = jn < BN / 64 ? jn : BN / 64;
       [[maybe_unused]] typename eng::side_of<Epi>::type side_next{};
-      // side data of the chunk after (tile, j): next chunk of this tile, else first chunk of this CTA's next tile
-      auto prefetch_side = [&](int j) {
-        if constexpr (HAS_SIDE) {
-          if (j + 1 < jmax) side_next = epi.pre(b, m, n0 + (2 * (j + 1) + half) * 32);
-          else if (nx.valid) side_next = epi.pre(nx.b, nx.m0 + q4 * 32 + lane, nx.n0 + half * 32);
+      // side data / input chunk of the chunk after (tile, j): next chunk of this tile, else the first chunk of this
+      // CTA's next tile
+      auto prefetch_next = [&](int j) {
+        if (j + 1 < jmax) {
+          if constexpr (HAS_SIDE) side_next = epi.pre(b, m, n0 + (2 * (j + 1) + half) * 32);
+          issue_in(slab + 1, b, m0 + q4 * 32, n0 + (2 * (j + 1) + half) * 32);
+        } else if (nx.valid) {
+          if constexpr (HAS_SIDE) side_next = epi.pre(nx.b, nx.m0 + q4 * 32 + lane, nx.n0 + half * 32);
+          issue_in(slab + 1, nx.b, nx.m0 + q4 * 32, nx.n0 + half * 32);
         }
       };
       auto release_tmem = [&]() {      // accumulator drained: hand the TMEM buffer back to the leader's MMA warp
@@ -280,26 +311,32 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader[buf]);
       };
-      // Per-warp staging of the output chunk, no cross-warp barrier: this warp's [32 rows x 32 cols] bf16 chunk goes
-      // through one of its two private 2 KB buffers (64-byte rows, SWIZZLE_64B: 16-byte unit u of row r sits at
-      // u ^ ((r >> 1) & 3)) and leaves with its own TMA store.  Lane 0 waits (after committing store g) until store
-      // g-1 has been read, so the other buffer is free before anybody writes chunk g+1 into it.
-      auto store_chunk = [&](const float* v, int c) {
-        if constexpr (TMA_OUT) {
-          uint8_t* wbuf = out_smem + (warp - kEpiWarp0) * (2 * L::kOutChunkBytes) + (slab & 1) * L::kOutChunkBytes;
-          const uint32_t rowbase = ptx::smem_u32(wbuf) + lane * 64;
-          const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+      // Per-warp staging of the output chunk(s), no cross-warp barrier: this warp's [32 rows x 32 cols] bf16 chunk
+      // goes through one of its two private 2 KB buffers (64-byte rows, SWIZZLE_64B: 16-byte unit u of row r sits
+      // at u ^ ((r >> 1) & 3)) and leaves with its own TMA store.  Lane 0 waits (after committing the stores of chunk
+      // g) until those of chunk g-1 have been read, so the other buffer is free before anybody writes chunk g+1.
+      const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+      auto stage_rows = [&](uint8_t* wbuf, const float* v) {
+        const uint32_t rowbase = ptx::smem_u32(wbuf) + lane * 64;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t addr = rowbase + ((static_cast<uint32_t>(t) ^ sw) << 4);
-            ptx::st_shared_v4(addr, ptx::pack_bf16x2(v[8 * t + 0], v[8 * t + 1]), ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]),
-                              ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]), ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
-          }
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t addr = rowbase + ((static_cast<uint32_t>(t) ^ sw) << 4);
+          ptx::st_shared_v4(addr, ptx::pack_bf16x2(v[8 * t + 0], v[8 * t + 1]), ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]),
+                            ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]), ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+        }
+      };
+      auto store_chunk = [&](const float* v, [[maybe_unused]] const float* v2, int c) {
+        if constexpr (TMA_OUT) {
+          uint8_t* wbuf = out_smem + (ew * 2 + (slab & 1)) * L::kOutChunkBytes;
+          uint8_t* wbuf2 = out2_smem + (ew * 2 + (slab & 1)) * L::kOutChunkBytes;
+          stage_rows(wbuf, v);
+          if constexpr (TMA_OUT2) stage_rows(wbuf2, v2);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           PF_MARK(pf_sts)
           if (lane == 0) {
             ptx::tma_store_3d(&maps.out, wbuf, n0 + c * 32, m0 + q4 * 32, b);
+            if constexpr (TMA_OUT2) ptx::tma_store_3d(&maps.out2, wbuf2, n0 + c * 32, m0 + q4 * 32, b);
             ptx::bulk_commit_group();
             ptx::bulk_wait_group_read<1>();
           }
@@ -308,7 +345,6 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
 #ifdef CLIPK_EPI_PROF
           ++pf_chunks;
 #endif
-          ++slab;
         }
       };
       if constexpr (DUAL) {
@@ -318,7 +354,7 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
           float v[32], v1[32];
           ptx::tmem_ld_32x32(tacc + c * 32, v);
           ptx::tmem_ld_32x32(tacc + BN + c * 32, v1);
-          prefetch_side(j);
+          prefetch_next(j);
           ptx::tmem_ld_wait();
           PF_MARK(pf_ld)
           if (j == jmax - 1) release_tmem();
@@ -326,18 +362,39 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
           else epi.chunk2(b, m, n0 + c * 32, v, v1);
           PF_MARK(pf_math)
           if constexpr (HAS_SIDE) side = side_next;
-          store_chunk(v, c);
+          store_chunk(v, nullptr, c);
+          ++slab;
         }
       } else {
         // single accumulator: the TMEM load of chunk j+1 is in flight while chunk j is processed (ping-pong registers)
         auto process = [&](float* v, int j) {
           const int c = 2 * j + half;
-          prefetch_side(j);
-          if constexpr (HAS_SIDE) epi.chunk(b, m, n0 + c * 32, v, side);
-          else epi.chunk(b, m, n0 + c * 32, v);
-          PF_MARK(pf_math)
-          if constexpr (HAS_SIDE) side = side_next;
-          store_chunk(v, c);
+          prefetch_next(j);
+          if constexpr (TMA_OUT2 || CHUNK_IN) {
+            [[maybe_unused]] uint32_t in[16];
+            [[maybe_unused]] float v2[32];
+            if constexpr (CHUNK_IN) {
+              ptx::mbar_wait(&in_bar[ew * 2 + (slab & 1)], (slab >> 1) & 1);
+              const uint32_t rowbase = ptx::smem_u32(in_smem + (ew * 2 + (slab & 1)) * L::kOutChunkBytes) + lane * 64;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint4 q = ptx::ld_shared_v4(rowbase + ((static_cast<uint32_t>(t) ^ sw) << 4));
+                in[4 * t] = q.x; in[4 * t + 1] = q.y; in[4 * t + 2] = q.z; in[4 * t + 3] = q.w;
+              }
+              __syncwarp();                    // everybody has read the buffer before lane 0 re-arms it (next chunk + 1)
+            }
+            epi.chunk(b, m, n0 + c * 32, v, side, in, v2);
+            PF_MARK(pf_math)
+            side = side_next;
+            store_chunk(v, v2, c);
+          } else {
+            if constexpr (HAS_SIDE) epi.chunk(b, m, n0 + c * 32, v, side);
+            else epi.chunk(b, m, n0 + c * 32, v);
+            PF_MARK(pf_math)
+            if constexpr (HAS_SIDE) side = side_next;
+            store_chunk(v, nullptr, c);
+          }
+          ++slab;
         };
         float va[32], vb[32];
         ptx::tmem_ld_32x32(tacc + half * 32, va);

@@ -39,6 +39,15 @@ struct epi_dual : std::false_type {};
 template <class E>
 struct epi_dual<E, std::void_t<decltype(E::kDual)>> : std::bool_constant<E::kDual> {};
 
+template <class E, class = void>
+struct epi_tma_out2 : std::false_type {};
+template <class E>
+struct epi_tma_out2<E, std::void_t<decltype(E::kTmaOut2)>> : std::bool_constant<E::kTmaOut2> {};
+template <class E, class = void>
+struct epi_chunk_in : std::false_type {};
+template <class E>
+struct epi_chunk_in<E, std::void_t<decltype(E::kChunkIn)>> : std::bool_constant<E::kChunkIn> {};
+
 // Epi::Side (optional): per-chunk side data that `Side pre(b, m, n)` loads ahead of time and chunk() consumes
 template <class E, class = void>
 struct epi_has_side : std::false_type {};
@@ -72,6 +81,8 @@ struct OperandMaps {
   CUtensorMap a[2];
   CUtensorMap b[2];
   CUtensorMap out;
+  CUtensorMap out2;   // second bf16 output of the same extent   (Epi::kTmaOut2, CTA-pair engine only)
+  CUtensorMap in;     // bf16 input of the output's extent, one [32 x 32] box per epilogue chunk (Epi::kChunkIn)
 };
 
 struct Problem {

@@ -13,9 +13,9 @@
 //
 //  forward :  K1  A = act(T V_i^T)            (epilogue PaclAct: also num = <u, t^>; A leaves the SM by TMA store)
 //             K2  u = A V_i  -> usq = |u|^2   (epilogue Usq: u never stored)
-//  backward:  K1  (recompute A)               K2' Gn = -beta u                   (epilogue GNeg, TMA store)
-//             K4  dual accumulators x = T V_i^T (recomputed), d = Gn V_i^T -> E, dsdot   (epilogue DsDual: reads no
-//                 activation tensor back from memory)
+//  backward:  K1' (recompute A, also X = <t^,V>: epilogue PaclActS)   K2' Gn = -beta u   (epilogue GNeg, TMA store)
+//             K4  d = Gn V_i^T  -> E, dsdot   (epilogue DsIn: the X chunk of each accumulator chunk arrives by TMA,
+//                 E overwrites X in place)
 //             K5  dt^ += E V                  (K folds (image, patch); fp32 accumulate)
 //             K6  dV_i = A^T Gn + E^T T^ - rnV^2 dsdot V      (two operand pairs, epilogue DvOut, TMA store)
 //  with G_ik = alpha_ik t^_k - beta_ik u_ik the gradient w.r.t. the pooled vector, E = ds rnV + alpha a and
@@ -190,7 +190,7 @@ template <int BN, bool A_MN, bool B_MN, class Epi>
 static int gemm_on(bool pair, const OperandDesc* a, const OperandDesc* b, int npairs, const int* ks, const int* ksub,
                    int M, int N, int batches, const typename Epi::Params& ep, cudaStream_t st) {
   if constexpr (!B_MN || BN % 128 == 0) {
-    if (pair && M > eng::BM) return launch_gemm2<BN, A_MN, B_MN, Epi>(a, b, npairs, ks, ksub, M, N, batches, ep, st);
+    if (pair) return launch_gemm2<BN, A_MN, B_MN, Epi>(a, b, npairs, ks, ksub, M, N, batches, ep, st);
   }
   return launch_gemm<BN, A_MN, B_MN, Epi>(a, b, npairs, ks, ksub, M, N, batches, ep, st);
 }
@@ -339,8 +339,22 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     const float* alpha0 = sh.alpha + (int64_t)i0 * Bt;
     const float* beta0 = sh.beta + (int64_t)i0 * Bt;
     float* dsdot0 = sh.dsdot + (int64_t)i0 * P;
-    // K1 (recompute activations)
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV0, rnT, w, nullptr, ls));
+    // K1' (recompute activations A; also X = bf16(<t^_k, V_ip>) into the E buffer, consumed in place by K4)
+    {
+      OperandDesc a, b;
+      a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
+      b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
+      const int ks[1] = {(D + 63) / 64};
+      const eng::OutDesc oa{w.A, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
+      const eng::OutDesc ox{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
+      epi::PaclActS::Params ep{oa, ox, rnV0, rnT, Bt, P, Ppad, act};
+      switch (pick_bn(Ppad)) {
+        case 256: CLIPK_TRY((launch_gemm2<256, false, false, epi::PaclActS>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        case 192: CLIPK_TRY((launch_gemm2<192, false, false, epi::PaclActS>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        case 128: CLIPK_TRY((launch_gemm2<128, false, false, epi::PaclActS>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        default: CLIPK_TRY((launch_gemm2<64, false, false, epi::PaclActS>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+      }
+    }
     // K2': Gn = -beta u
     {
       OperandDesc a, b;
@@ -349,18 +363,19 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       epi::GNeg::Params ep{{w.G, D, (int64_t)Bt * D, Bt, D, gi}, beta0, Bt};
       CLIPK_TRY(launch_nd<epi::GNeg, false>((engine2_mask() & kK2) != 0, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
     }
-    // K4 (dual): x = T V^T (recomputed), d = Gn V^T  ->  E, dsdot
+    // K4: d = Gn V^T; with the X chunks read back through TMA  ->  E (in place over X), dsdot
     {
-      OperandDesc a[2], b;
-      a[0].ptr = T; a[0].rows = Bt; a[0].k = D; a[0].ld = D; a[0].batch = 1; a[0].bmul = 0;
-      a[1].ptr = w.G; a[1].rows = Bt; a[1].k = D; a[1].ld = D; a[1].batch = gi; a[1].batch_stride = (int64_t)Bt * D; a[1].bmul = 1;
+      OperandDesc a, b;
+      a.ptr = w.G; a.rows = Bt; a.k = D; a.ld = D; a.batch = gi; a.batch_stride = (int64_t)Bt * D; a.bmul = 1;
       b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
       const int ks[1] = {(D + 63) / 64};
-      epi::DsDual::Params ep{{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, alpha0, dsdot0, Bt, P, Ppad, act};
-      if (Ppad % 128 == 0 || Ppad > 64) {
-        CLIPK_TRY((gemm_on<128, false, false, epi::DsDual>((engine2_mask() & kK4) != 0, a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
-      } else {
-        CLIPK_TRY((gemm_on<64, false, false, epi::DsDual>((engine2_mask() & kK4) != 0, a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
+      const eng::OutDesc oe{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
+      epi::DsIn::Params ep{oe, oe, rnV0, alpha0, dsdot0, Bt, P, Ppad, act};
+      switch (pick_bn(Ppad)) {
+        case 256: CLIPK_TRY((launch_gemm2<256, false, false, epi::DsIn>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        case 192: CLIPK_TRY((launch_gemm2<192, false, false, epi::DsIn>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        case 128: CLIPK_TRY((launch_gemm2<128, false, false, epi::DsIn>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
+        default: CLIPK_TRY((launch_gemm2<64, false, false, epi::DsIn>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
       }
     }
     // K5: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (K folds image and patch; split-K over images so that

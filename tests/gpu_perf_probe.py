@@ -111,6 +111,9 @@ if __name__ == "__main__":
         gemm(4096, 192, 4096, nb=16)
         gemm(4096, 128, 4096, nb=32)
         gemm(4096, 64, 4096, nb=64)
+    if cmd == "bn2":        # MMA cost versus N: 592 pair-tiles (8 full waves of 74 clusters), K = 4096
+        for n in (256, 224, 192, 160, 128, 96, 64):
+            gemm(4096, n, 4096, nb=37)
     if cmd == "trace":      # run with CLIPK_TRACE=1
         B, grp = int(sys.argv[2]), int(sys.argv[3])
         allpairs_once(B, 576, 768, grp)
