@@ -201,7 +201,8 @@ struct StoreTma {
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1
 // acc[m=text k][n=patch p] = <T_k, V_ip> (raw).  s = acc * rnT[k] * rnV[i,p];  a = sigmoid(10 s)  (pacl.py:133)
-// output (TMA store): A bf16 [batch][M][Ppad], zero in the pad columns;
+// output (TMA store): A bf16 [batch][M][Ppad]; columns >= P are never written (the output map's extent is P) and
+// never read (the operand maps of the consumers have extent P: TMA zero-fills beyond it);
 // side output: num[i,k] += sum_p a * <t^_k, V_ip> = <u_ik, t^_k>.
 // Side data: lane l holds rnV[i, n + l] of the chunk (one coalesced load issued a chunk ahead, broadcast by shuffle).
 __device__ __forceinline__ void bf16_round_pair(float& a0, float& a1) {
@@ -254,11 +255,6 @@ struct PaclAct {
         v[j] = a0;
         v[j + 1] = a1;
       }
-    }
-    if (n + 32 > p.P) {                            // chunk straddles the end of the patch axis: zero the pad columns
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n + j >= p.P) v[j] = 0.f;              // (their acc contribution is already 0: TMA zero-fills V rows >= P)
     }
   }
   __device__ void tile_end(int b, int m, int, int, int) {
@@ -401,24 +397,26 @@ struct PaclActS {
     const int lane = (int)ptx::lane_id();
     return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
   }
-  __device__ void chunk(int, int, int n, float* v, const Side& rn_l, const uint32_t*, float* x) {
-    const bool ones = p.act == CLIPK_ACT_ONES;
+  __device__ void chunk(int, int, int, float* v, const Side& rn_l, const uint32_t*, float* x) {
+    if (p.act == CLIPK_ACT_ONES) {                       // warp-uniform
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        x[j] = v[j] * rt;
+        v[j] = 1.f;
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const float r0 = __shfl_sync(0xffffffffu, rn_l, j);
       const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
-      x[j] = v[j] * rt;                                    // pad columns: V rows >= P are zero-filled -> 0
+      x[j] = v[j] * rt;                                    // X = <t^_k, V_ip>
       x[j + 1] = v[j + 1] * rt;
       float t0, t1;
       asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v[j] * rt5 * r0));
       asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v[j + 1] * rt5 * r1));
-      v[j] = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
-      v[j + 1] = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
-    }
-    if (n + 32 > p.P) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n + j >= p.P) v[j] = 0.f;
+      v[j] = fmaf(0.5f, t0, 0.5f);
+      v[j + 1] = fmaf(0.5f, t1, 0.5f);
     }
   }
   __device__ void tile_end(int, int, int, int, int) {}
@@ -452,36 +450,39 @@ struct DsIn {
   }
   __device__ void chunk(int b, int m, int n, float* d, const Side& rn_l, const uint32_t* in, float*) {
     const int lane = (int)ptx::lane_id();
-    const bool ones = p.act == CLIPK_ACT_ONES;
-    const float gate = (m < p.M && !ones) ? 10.f : 0.f;
+    const int col = n + lane;
+    if (p.act == CLIPK_ACT_ONES) {                       // warp-uniform: a = 1, ds = 0  ->  E = alpha, dsdot untouched
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = al;
+      return;
+    }
+    // All factors of 5 are folded:  r5 = 5 rnV,  s5 = 5 s = X r5,  ds5 = ds / 5 = da * 2 a (1 - a)
+    //   E = alpha a + ds rnV = alpha a + ds5 r5          ds * s = ds5 * s5
+    const float r5_l = 5.f * rn_l;                       // 0 for p >= P: masks the pad columns
+    const float g2 = m < p.M ? 2.f : 0.f;
     float dss[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      const float r0 = __shfl_sync(0xffffffffu, rn_l, j);        // 0 for p >= P: masks the pad columns
-      const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+      const float r0 = __shfl_sync(0xffffffffu, r5_l, j);
+      const float r1 = __shfl_sync(0xffffffffu, r5_l, j + 1);
       const float x0 = __uint_as_float(in[j >> 1] << 16);
       const float x1 = __uint_as_float(in[j >> 1] & 0xFFFF0000u);
       const float s0 = x0 * r0, s1 = x1 * r1;
       float t0, t1;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(5.f * s0));
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(5.f * s1));
-      float a0 = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
-      float a1 = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(s0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(s1));
+      float a0 = fmaf(0.5f, t0, 0.5f);
+      float a1 = fmaf(0.5f, t1, 0.5f);
       bf16_round_pair(a0, a1);
-      const float ds0 = fmaf(al, x0, d[j]) * gate * a0 * (1.f - a0);
-      const float ds1 = fmaf(al, x1, d[j + 1]) * gate * a1 * (1.f - a1);
-      d[j] = fmaf(al, a0, ds0 * r0);                              // E
-      d[j + 1] = fmaf(al, a1, ds1 * r1);
-      dss[j] = ds0 * s0;                                          // ds * s  (0 in pad columns / invalid rows)
+      const float u0 = a0 * g2, u1 = a1 * g2;
+      const float ds0 = fmaf(al, x0, d[j]) * fmaf(-u0, a0, u0);        // da * 2 a (1 - a)
+      const float ds1 = fmaf(al, x1, d[j + 1]) * fmaf(-u1, a1, u1);
+      d[j] = fmaf(ds0, r0, al * a0);                                   // E
+      d[j + 1] = fmaf(ds1, r1, al * a1);
+      dss[j] = ds0 * s0;                                               // ds * s  (0 in pad columns / invalid rows)
       dss[j + 1] = ds1 * s1;
     }
-    if (n + 32 > p.P) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n + j >= p.P) d[j] = 0.f;
-    }
     const float cs = ptx::warp_colsum32(dss);   // lane j: sum over this warp's 32 rows of column n + j
-    const int col = n + lane;
     if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
   }
   __device__ void tile_end(int, int, int, int, int) {}
@@ -508,7 +509,7 @@ struct DvOut {
     coef = 0.f;
     if (m < p.M) {
       const float r = __ldg(p.rnV + (int64_t)b * p.M + m);
-      coef = r * r * __ldg(p.dsdot + (int64_t)b * p.M + m);
+      coef = r * r * __ldcg(p.dsdot + (int64_t)b * p.M + m);   // L2: may have been written earlier in this kernel
     }
   }
   __device__ Side pre(int b, int m, int n) const {

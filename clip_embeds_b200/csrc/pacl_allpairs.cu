@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "epilogues.cuh"
+#include "allpairs_mega.cuh"
 #include "simt_util.cuh"
 
 namespace clipk {
@@ -213,7 +214,7 @@ static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, in
   a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
   b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
   const int ks[1] = {(D + 63) / 64};
-  epi::PaclAct::Params ep{{w.A, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi}, rnV0, rnT, num0, Bt, P, Ppad, act};
+  epi::PaclAct::Params ep{{w.A, Ppad, (int64_t)Bt * Ppad, Bt, P, gi}, rnV0, rnT, num0, Bt, P, Ppad, act};   // extent P: pads clipped
   const bool pair = (engine2_mask() & kK1) != 0;
   switch (pick_bn(Ppad)) {
     case 256: return gemm_on<256, false, false, epi::PaclAct>(pair, &a, &b, 1, ks, ks, Bt, Ppad, gi, ep, st);
@@ -227,7 +228,7 @@ static int launch_k1(const __nv_bfloat16* T, const __nv_bfloat16* V0, int gi, in
 static void k2_operands(const ApWorkspace& w, const __nv_bfloat16* V0, int gi, int Bt, int P, int D, OperandDesc* a,
                         OperandDesc* b) {
   const int Ppad = round_up(P, 64);
-  a->ptr = w.A; a->rows = Bt; a->k = Ppad; a->ld = Ppad; a->batch = gi; a->batch_stride = (int64_t)Bt * Ppad; a->bmul = 1;
+  a->ptr = w.A; a->rows = Bt; a->k = P; a->ld = Ppad;   /* extent P: TMA zero-fills the pad columns */ a->batch = gi; a->batch_stride = (int64_t)Bt * Ppad; a->bmul = 1;
   a->reverse = 1;   // K1 walked the images upwards; start with the activations it wrote last
   b->ptr = V0; b->mn_major = true; b->rows = D; b->k = P; b->ld = D; b->batch = gi; b->batch_stride = (int64_t)P * D; b->bmul = 1;
 }
@@ -248,7 +249,6 @@ static int validate(int Bi, int Bt, int P, int D, int act, int group) {
   CLIPK_REQUIRE(Bi > 0 && Bt > 0 && P > 0 && D > 0, "pacl_allpairs: empty problem (Bi=%d Bt=%d P=%d D=%d)", Bi, Bt, P, D);
   CLIPK_REQUIRE(D % 8 == 0, "pacl_allpairs: D=%d must be a multiple of 8 (16-byte rows for TMA)", D);
   CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES, "pacl_allpairs: bad activation %d", act);
-  CLIPK_REQUIRE(group >= 1, "pacl_allpairs: group must be >= 1");
   return 0;
 }
 
@@ -265,10 +265,203 @@ static int join_lanes(LanePool* lp, int lanes, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ mega path
+// One persistent kernel per direction (allpairs_mega.cuh).  `group` < 0: -group images per group; 0: automatic.
+struct MegaPlan {
+  int gs, depth, slots, ngroups;
+};
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+static MegaPlan mega_plan(int Bi, int Bt, int P, int D, int group, int lanes, int backward) {
+  MegaPlan pl;
+  const int Ppad = round_up(P, 64);
+  int gs = group < 0 ? -group : env_int("CLIPK_MEGA_GS", 0);
+  pl.depth = lanes > 0 && group < 0 ? lanes : env_int("CLIPK_MEGA_DEPTH", 2);
+  if (gs <= 0) {
+    // keep the live scratch (slots groups of A [+ E + G]) around 72 MB so that it stays in the 126 MB L2 next to V
+    const double per_img = (double)Bt * (backward ? (2.0 * Ppad + D) : (double)Ppad) * 2.0;
+    gs = (int)(72e6 / ((pl.depth + 1) * per_img));
+    if (gs < 1) gs = 1;
+    if (gs > 16) gs = 16;
+  }
+  if (gs > Bi) gs = Bi;
+  pl.gs = gs;
+  pl.ngroups = (Bi + gs - 1) / gs;
+  if (pl.depth > pl.ngroups) pl.depth = pl.ngroups;
+  if (pl.depth < 1) pl.depth = 1;
+  pl.slots = env_int("CLIPK_MEGA_SLOTS", pl.depth + 1);
+  if (pl.slots < pl.depth) pl.slots = pl.depth;
+  return pl;
+}
+
+struct MegaWs {
+  __nv_bfloat16 *A, *E, *G, *That;
+  float *dsdot, *alpha, *beta, *dth;
+  unsigned* done;
+};
+static size_t mega_carve(MegaWs* w, void* base, const MegaPlan& pl, int Bi, int Bt, int P, int D, int backward) {
+  const int Ppad = round_up(P, 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  };
+  const size_t S = (size_t)pl.slots * pl.gs;
+  w->A = static_cast<__nv_bfloat16*>(take(S * Bt * Ppad * 2));
+  w->done = static_cast<unsigned*>(take((size_t)pl.ngroups * mega::kMaxPhases * 4));
+  if (backward) {
+    w->E = static_cast<__nv_bfloat16*>(take(S * Bt * Ppad * 2));
+    w->G = static_cast<__nv_bfloat16*>(take(S * Bt * D * 2));
+    w->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
+    w->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
+    w->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    w->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
+    w->dth = static_cast<float*>(take((size_t)Bt * D * 4));
+  }
+  return off;
+}
+
+static int mega_launch(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
+                       const float* rnV, const float* rnT, float* num, float* usq, __nv_bfloat16* dV,
+                       const MegaWs& w, const MegaPlan& pl, int backward, cudaStream_t st) {
+  const int Ppad = round_up(P, 64);
+  const uint64_t S = (uint64_t)pl.slots * pl.gs;
+  mega::Maps mp;
+  memset(&mp, 0, sizeof(mp));
+  const uint64_t ldP = (uint64_t)Ppad * 2, ldD = (uint64_t)D * 2;
+  CLIPK_TRY(make_tmap_bf16(&mp.T_k, T, D, Bt, 1, ldD, 0, 128));
+  CLIPK_TRY(make_tmap_bf16(&mp.V_k, V, D, P, Bi, ldD, (uint64_t)P * ldD, mega::kBNP / 2));
+  CLIPK_TRY(make_tmap_bf16(&mp.V_mn, V, D, P, Bi, ldD, (uint64_t)P * ldD, 64));
+  CLIPK_TRY(make_tmap_bf16(&mp.A_k, w.A, P, Bt, S, ldP, (uint64_t)Bt * ldP, 128));     // extent P: pads read as zero
+  CLIPK_TRY(make_tmap_bf16_box(&mp.oA, w.A, P, Bt, S, ldP, (uint64_t)Bt * ldP, 32, 32));
+  if (backward) {
+    CLIPK_TRY(make_tmap_bf16(&mp.A_mn, w.A, P, Bt, S, ldP, (uint64_t)Bt * ldP, 64));
+    CLIPK_TRY(make_tmap_bf16(&mp.E_k, w.E, P, Bt, S, ldP, (uint64_t)Bt * ldP, 128));
+    CLIPK_TRY(make_tmap_bf16(&mp.E_mn, w.E, P, Bt, S, ldP, (uint64_t)Bt * ldP, 64));
+    CLIPK_TRY(make_tmap_bf16(&mp.G_k, w.G, D, Bt, S, ldD, (uint64_t)Bt * ldD, 128));
+    CLIPK_TRY(make_tmap_bf16(&mp.G_mn, w.G, D, Bt, S, ldD, (uint64_t)Bt * ldD, 64));
+    CLIPK_TRY(make_tmap_bf16(&mp.Th_mn, w.That, D, Bt, 1, ldD, 0, 64));
+    CLIPK_TRY(make_tmap_bf16_box(&mp.oE, w.E, P, Bt, S, ldP, (uint64_t)Bt * ldP, 32, 32));
+    CLIPK_TRY(make_tmap_bf16_box(&mp.oG, w.G, D, Bt, S, ldD, (uint64_t)Bt * ldD, 32, 32));
+    CLIPK_TRY(make_tmap_bf16_box(&mp.odV, dV, D, P, Bi, ldD, (uint64_t)P * ldD, 32, 32));
+  }
+  mega::Sched sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.Bi = Bi; sc.Bt = Bt; sc.P = P; sc.Ppad = Ppad; sc.D = D; sc.act = act;
+  sc.gs = pl.gs; sc.ngroups = pl.ngroups; sc.depth = pl.depth; sc.slots = pl.slots;
+  const int tmT = (Bt + 255) / 256, tmP = (P + 255) / 256;
+  const int tnP = (Ppad + mega::kBNP - 1) / mega::kBNP, tnD = (D + mega::kBND - 1) / mega::kBND;
+  for (int i = 0; i < mega::kMaxPhases; ++i) { sc.dep_same[i] = -1; sc.dep_ring[i][0] = sc.dep_ring[i][1] = -1; }
+  if (!backward) {
+    sc.nph = 2;
+    sc.ph[0] = mega::PH_ACT; sc.tm[0] = tmT; sc.tn[0] = tnP; sc.dep_ring[0][0] = 1;
+    sc.ph[1] = mega::PH_USQ; sc.tm[1] = tmT; sc.tn[1] = tnD; sc.dep_same[1] = 0;
+  } else {
+    sc.nph = 5;
+    sc.ph[0] = mega::PH_ACTS; sc.tm[0] = tmT; sc.tn[0] = tnP; sc.dep_ring[0][0] = 3; sc.dep_ring[0][1] = 4;
+    sc.ph[1] = mega::PH_GNEG; sc.tm[1] = tmT; sc.tn[1] = tnD; sc.dep_same[1] = 0;
+    sc.ph[2] = mega::PH_DS; sc.tm[2] = tmT; sc.tn[2] = tnP; sc.dep_same[2] = 1;
+    sc.ph[3] = mega::PH_DT; sc.tm[3] = tmT; sc.tn[3] = tnD; sc.dep_same[3] = 2;
+    sc.ph[4] = mega::PH_DV; sc.tm[4] = tmP; sc.tn[4] = tnD; sc.dep_same[4] = 2;
+  }
+  sc.dt_spb = env_int("CLIPK_MEGA_DTSPB", pl.gs);      // images folded into one DT tile's K range
+  if (sc.dt_spb < 1) sc.dt_spb = 1;
+  long long total = 0;
+  for (int g = 0; g < pl.ngroups; ++g)
+    for (int i = 0; i < sc.nph; ++i) total += mega::job_tiles(sc, i, g);
+  CLIPK_REQUIRE(total < 0x3fffffff, "pacl_allpairs: tile sequence too long (%lld)", total);
+  sc.total_tiles = (int)total;
+  sc.done = w.done;
+  sc.rnV = rnV; sc.rnT = rnT; sc.num = num; sc.usq = usq;
+  sc.alpha = w.alpha; sc.beta = w.beta; sc.dsdot = w.dsdot; sc.dth = w.dth;
+  sc.V = V; sc.c = c;
+  sc.flags = env_int("CLIPK_MEGA_FLAGS", 0);
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.done, 0, (size_t)pl.ngroups * mega::kMaxPhases * 4, st));
+  static std::atomic<uint64_t> attr_mask{0};
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(mega::allpairs_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          mega::kSmemTotal));
+    attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (sc.total_tiles < pairs ? sc.total_tiles : pairs);
+  const bool tr = trace_enabled();
+  if (tr) trace_begin(backward ? "allpairs_mega_kernel (backward)" : "allpairs_mega_kernel (forward)", st);
+  mega::allpairs_mega_kernel<<<grid, mega::kThreads, mega::kSmemTotal, st>>>(mp, sc);
+  if (tr) trace_end(st);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dT_k = rnT_k (dth_k - t^_k <t^_k, dth_k>) from a single accumulated dt^ buffer
+__global__ void dtext_finalize1_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT,
+                                       const float* __restrict__ dth, int Bt, int D, float* __restrict__ dT) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Bt) return;
+  const int lane = threadIdx.x & 31;
+  const float rt = rnT[row];
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32)
+    dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, dth[(int64_t)row * D + d], dot);
+  dot = ptx::warp_sum(dot);
+  for (int d = lane; d < D; d += 32) {
+    const float th = __bfloat162float(T[(int64_t)row * D + d]) * rt;
+    dT[(int64_t)row * D + d] = rt * (dth[(int64_t)row * D + d] - th * dot);
+  }
+}
+
+static int mega_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
+                    float* rnV, float* rnT, float* num, float* usq, float* scores, void* ws, size_t ws_bytes, int group,
+                    int lanes, cudaStream_t st) {
+  const MegaPlan pl = mega_plan(Bi, Bt, P, D, group, lanes, 0);
+  MegaWs w{};
+  const size_t need = mega_carve(&w, ws, pl, Bi, Bt, P, D, 0);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
+  rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
+  count_launches(2);
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
+  CLIPK_TRY(mega_launch(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, nullptr, w, pl, 0, st));
+  const int64_t n = (int64_t)Bi * Bt;
+  allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int mega_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
+                    const float* rnV, const float* rnT, const float* num, const float* usq, const float* dscores,
+                    __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, int lanes, cudaStream_t st) {
+  const MegaPlan pl = mega_plan(Bi, Bt, P, D, group, lanes, 1);
+  MegaWs w{};
+  const size_t need = mega_carve(&w, ws, pl, Bi, Bt, P, D, 1);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int64_t n = (int64_t)Bi * Bt;
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dsdot, 0, (size_t)Bi * P * 4, st));
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.dth, 0, (size_t)Bt * D * 4, st));
+  allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, w.alpha, w.beta);
+  that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, w.That);
+  count_launches(2);
+  CLIPK_TRY(mega_launch(V, T, Bi, Bt, P, D, act, c, rnV, rnT, const_cast<float*>(num), const_cast<float*>(usq), dV, w,
+                        pl, 1, st));
+  dtext_finalize1_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, w.dth, Bt, D, dT);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  float* rnV, float* rnT, float* num, float* usq, float* scores, void* ws, size_t ws_bytes, int group,
                  int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
+  if (group <= 0) return mega_fwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, scores, ws, ws_bytes, group, lanes, st);
   CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
   ApWorkspace w[kMaxLanes]{};
   ApShared sh{};
@@ -310,6 +503,8 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
                  const float* rnV, const float* rnT, const float* num, const float* usq, const float* dscores,
                  __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
+  if (group <= 0)
+    return mega_bwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, dscores, dV, dT, ws, ws_bytes, group, lanes, st);
   CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
   ApWorkspace wl[kMaxLanes]{};
   ApShared sh{};
@@ -345,8 +540,8 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       a.ptr = T; a.rows = Bt; a.k = D; a.ld = D; a.batch = 1; a.bmul = 0;
       b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
       const int ks[1] = {(D + 63) / 64};
-      const eng::OutDesc oa{w.A, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
-      const eng::OutDesc ox{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
+      const eng::OutDesc oa{w.A, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // extent P: pad columns are clipped on store
+      const eng::OutDesc ox{w.E, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // and zero-filled on load
       epi::PaclActS::Params ep{oa, ox, rnV0, rnT, Bt, P, Ppad, act};
       switch (pick_bn(Ppad)) {
         case 256: CLIPK_TRY((launch_gemm2<256, false, false, epi::PaclActS>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
@@ -369,7 +564,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       a.ptr = w.G; a.rows = Bt; a.k = D; a.ld = D; a.batch = gi; a.batch_stride = (int64_t)Bt * D; a.bmul = 1;
       b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
       const int ks[1] = {(D + 63) / 64};
-      const eng::OutDesc oe{w.E, Ppad, (int64_t)Bt * Ppad, Bt, Ppad, gi};
+      const eng::OutDesc oe{w.E, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};
       epi::DsIn::Params ep{oe, oe, rnV0, alpha0, dsdot0, Bt, P, Ppad, act};
       switch (pick_bn(Ppad)) {
         case 256: CLIPK_TRY((launch_gemm2<256, false, false, epi::DsIn>(&a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls))); break;
@@ -385,7 +580,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       const int spb = (gi + want - 1) / want;                // images per split (last split may be shorter)
       const int nsplit = (gi + spb - 1) / spb;               // no empty split: an empty K range leaves TMEM undefined
       OperandDesc a, b;
-      a.ptr = w.E; a.rows = Bt; a.k = Ppad; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
+      a.ptr = w.E; a.rows = Bt; a.k = P; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
       a.sub_per_batch = spb;
       a.sub_total = gi;
       a.reverse = 1;   // K4 walked upwards: take the last-written E first
@@ -398,7 +593,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     // K6: dV_i = A_i^T Gn_i + E_i^T T^ - rnV^2 dsdot V
     {
       OperandDesc a[2], b[2];
-      a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = Ppad; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
+      a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = P; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
       a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
       a[0].reverse = 1;
       b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
@@ -424,6 +619,10 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
 extern "C" {
 
 size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int backward) {
+  if (group <= 0) {
+    clipk::MegaWs mw{};
+    return clipk::mega_carve(&mw, nullptr, clipk::mega_plan(Bi, Bt, P, D, group, lanes, backward), Bi, Bt, P, D, backward);
+  }
   clipk::ApWorkspace w[clipk::kMaxLanes]{};
   clipk::ApShared sh{};
   if (lanes < 1 || lanes > clipk::kMaxLanes) return 0;

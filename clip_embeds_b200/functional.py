@@ -110,11 +110,14 @@ def pacl_eval_scores(visual_proj, text_proj, c=100.0, activation="sigmoid"):
 
 # --------------------------------------------------------------------------------------------- all-pairs PACL
 def default_schedule(Bt, P, D, backward=True):
-    """(images per group, lanes).  See DESIGN.md "group scheduling": measured on B200 at the C2 shape."""
+    """(group, lanes) handed to the C ABI.  group 0 = the persistent dependency-driven kernel with an automatically
+    sized image group (DESIGN.md "mega kernel"); group < 0 = the same with -group images per group and `lanes` groups
+    in lock-step; group > 0 = the staged path (one engine launch per GEMM, `group` images per launch on `lanes`
+    internal streams)."""
     return _SCHEDULE["bwd" if backward else "fwd"]
 
 
-_SCHEDULE = {"fwd": (128, 1), "bwd": (128, 1)}
+_SCHEDULE = {"fwd": (128, 1), "bwd": (128, 1)}      # staged path; the persistent kernel (group <= 0) is opt-in
 
 
 def _resolve(group, Bi, Bt, P, D, backward):
@@ -124,6 +127,8 @@ def _resolve(group, Bi, Bt, P, D, backward):
         g, lanes = group
     else:
         g, lanes = int(group), 1
+    if g <= 0:
+        return max(g, -Bi), max(0, min(lanes, 8))
     return max(1, min(g, Bi)), max(1, min(lanes, 4))
 
 

@@ -124,7 +124,8 @@ if __name__ == "__main__":
         V = torch.randn(int(sys.argv[2]), 576, 768, device="cuda").to(torch.bfloat16)
         T = torch.randn(1024, 768, device="cuda").to(torch.bfloat16)
         with torch.no_grad():
-            Fk.pacl_scores(V, T, 10.0, "sigmoid", int(sys.argv[3]))
+            a = sys.argv[3]
+            Fk.pacl_scores(V, T, 10.0, "sigmoid", tuple(int(y) for y in a.split(":")) if ":" in a else int(a))
         torch.cuda.synchronize()
     if cmd == "cpu":
         import time
