@@ -117,7 +117,7 @@ def default_schedule(Bt, P, D, backward=True):
     return _SCHEDULE["bwd" if backward else "fwd"]
 
 
-_SCHEDULE = {"fwd": (128, 1), "bwd": (128, 1)}      # staged path; the persistent kernel (group <= 0) is opt-in
+_SCHEDULE = {"fwd": (128, 2), "bwd": (128, 2)}      # staged path; the persistent kernel (group <= 0) is opt-in
 
 
 def _resolve(group, Bi, Bt, P, D, backward):
