@@ -240,20 +240,25 @@ struct PaclAct {
         v[j] = 1.f;
       }
     } else {
+      // blocks of 8 columns, each stage over the whole block: 8 independent shuffle -> MUFU -> FMA chains in flight
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float r0 = __shfl_sync(0xffffffffu, rn_l, j);      // rnV of column j (per column; rt5 is per row)
-        const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
-        float t0, t1;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(v[j] * rt5 * r0));       // sigmoid(10 s) = 0.5 tanh(5 s) + 0.5
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(v[j + 1] * rt5 * r1));
-        float a0 = fmaf(0.5f, t0, 0.5f);
-        float a1 = fmaf(0.5f, t1, 0.5f);
-        bf16_round_pair(a0, a1);                   // the value the pooling GEMM will see
-        acc = fmaf(a0, v[j], acc);                 // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
-        acc = fmaf(a1, v[j + 1], acc);
-        v[j] = a0;
-        v[j + 1] = a1;
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        float r[8], a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __shfl_sync(0xffffffffu, rn_l, j0 + i);   // rnV of the column (rt5 is per row)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = v[j0 + i] * rt5 * r[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("tanh.approx.f32 %0, %1;" : "=f"(a[i]) : "f"(r[i]));   // sigmoid(10 s) = 0.5 tanh(5 s) + 0.5
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(0.5f, a[i], 0.5f);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) bf16_round_pair(a[i], a[i + 1]);               // the value the pooling GEMM will see
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc = fmaf(a[i], v[j0 + i], acc);        // sum_p a <T_k, V_p>   (scaled by rnT at tile end)
+          v[j0 + i] = a[i];
+        }
       }
     }
   }
@@ -530,6 +535,48 @@ struct DvOut {
         v[8 * j + 2 * t] = fmaf(nc, __uint_as_float(w[t] << 16), v[8 * j + 2 * t]);
         v[8 * j + 2 * t + 1] = fmaf(nc, __uint_as_float(w[t] & 0xFFFF0000u), v[8 * j + 2 * t + 1]);
       }
+    }
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, dV transposed
+// Same result as DvOut computed as dV_i^T: acc[m = d][n = patch p] = sum_k Gn_ik[d] a_ikp + sum_k T^_k[d] E_ikp, so
+// that M = D (a multiple of 256 for the CLIP widths) instead of M = P = 576 (which wastes a third of a 768-row cover).
+//   dV[i][p][d] = acc[d][p] - rnV_ip^2 dsdot_ip V[i][p][d]
+// The V chunk arrives by TMA as [32 p][32 d] (the output's layout); this lane owns column d of it and of the staged
+// output chunk.  Side: lane l holds coef = rnV^2 dsdot of patch n + l.
+struct DvOutT {
+  static constexpr bool kTmaOut = true;
+  static constexpr bool kChunkIn = true;
+  static constexpr bool kTransposed = true;
+  using Side = float;
+  struct Params {
+    eng::OutDesc out;         // dV [batch][P][D]
+    eng::OutDesc in;          // V  [batch][P][D]
+    const float* rnV;         // [batch][P]
+    const float* dsdot;       // [batch][P]
+    int P;
+  };
+  Params p;
+  __device__ explicit DvOutT(const Params& pp) : p(pp) {}
+  __device__ void tile_begin(int, int, int) {}
+  __device__ Side pre(int b, int, int n) const {
+    const int col = n + (int)ptx::lane_id();
+    if (col >= p.P) return 0.f;
+    const float r = __ldg(p.rnV + (int64_t)b * p.P + col);
+    return r * r * __ldcg(p.dsdot + (int64_t)b * p.P + col);     // dsdot was written earlier in this stream / kernel
+  }
+  __device__ void chunk_t(int, int, int, float* v, const Side& coef_l, uint32_t in_addr, uint32_t out_addr, int lane) {
+    // element (row j = patch, col = lane = d): 64-byte rows, 16-byte unit u of row j sits at u ^ ((j >> 1) & 3)
+    const uint32_t unit = static_cast<uint32_t>(lane) >> 3, within = (static_cast<uint32_t>(lane) & 7u) * 2u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint32_t off = j * 64 + ((unit ^ ((static_cast<uint32_t>(j) >> 1) & 3u)) << 4) + within;
+      const float cj = __shfl_sync(0xffffffffu, coef_l, j);
+      const float x = __uint_as_float(ptx::ld_shared_u16(in_addr + off) << 16);
+      const float o = fmaf(-cj, x, v[j]);
+      ptx::st_shared_u16(out_addr + off, ptx::pack_bf16x2(o, 0.f));
     }
   }
   __device__ void tile_end(int, int, int, int, int) {}

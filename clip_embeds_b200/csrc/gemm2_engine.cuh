@@ -100,6 +100,8 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   constexpr bool HAS_SIDE = epi_has_side<Epi>::value;
   constexpr bool TMA_OUT2 = eng::epi_tma_out2<Epi>::value;
   constexpr bool CHUNK_IN = eng::epi_chunk_in<Epi>::value;
+  constexpr bool TRANSPOSED = eng::epi_transposed<Epi>::value;
+  static_assert(!TRANSPOSED || (CHUNK_IN && TMA_OUT && !TMA_OUT2), "transposed epilogues: chunk-in + one output");
   static_assert(!TMA_OUT2 || TMA_OUT, "a second output needs the first");
   static_assert(!(TMA_OUT2 || CHUNK_IN) || (HAS_SIDE && !DUAL), "chunk-in / second output: uniform functors only");
   static_assert(BN % 32 == 0 && BN <= 256, "BN: multiple of 32, at most 256");
@@ -270,7 +272,10 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
         if (lane == 0) {
           uint64_t* bar = &in_bar[ew * 2 + (g & 1)];
           ptx::mbar_arrive_expect_tx(bar, L::kOutChunkBytes);
-          ptx::tma_load_3d(in_smem + (ew * 2 + (g & 1)) * L::kOutChunkBytes, &maps.in, bar, ncol, mrow0, bb);
+          if constexpr (TRANSPOSED)   // the input tensor is laid out like the output: [accumulator column][accumulator row]
+            ptx::tma_load_3d(in_smem + (ew * 2 + (g & 1)) * L::kOutChunkBytes, &maps.in, bar, mrow0, ncol, bb);
+          else
+            ptx::tma_load_3d(in_smem + (ew * 2 + (g & 1)) * L::kOutChunkBytes, &maps.in, bar, ncol, mrow0, bb);
         }
       }
     };
@@ -370,7 +375,24 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
         auto process = [&](float* v, int j) {
           const int c = 2 * j + half;
           prefetch_next(j);
-          if constexpr (TMA_OUT2 || CHUNK_IN) {
+          if constexpr (TRANSPOSED) {
+            // the functor reads its input chunk from / writes its output chunk to the staging buffers itself
+            // ([32 output rows][32 output cols] bf16, SWIZZLE_64B), one element per (row j, this lane's column)
+            ptx::mbar_wait(&in_bar[ew * 2 + (slab & 1)], (slab >> 1) & 1);
+            uint8_t* wbuf = out_smem + (ew * 2 + (slab & 1)) * L::kOutChunkBytes;
+            epi.chunk_t(b, m, n0 + c * 32, v, side, ptx::smem_u32(in_smem + (ew * 2 + (slab & 1)) * L::kOutChunkBytes),
+                        ptx::smem_u32(wbuf), lane);
+            PF_MARK(pf_math)
+            side = side_next;
+            ptx::fence_proxy_async_smem();
+            __syncwarp();                      // input buffer read by everybody, output chunk staged by everybody
+            if (lane == 0) {
+              ptx::tma_store_3d(&maps.out, wbuf, m0 + q4 * 32, n0 + c * 32, b);
+              ptx::bulk_commit_group();
+              ptx::bulk_wait_group_read<1>();
+            }
+            __syncwarp();
+          } else if constexpr (TMA_OUT2 || CHUNK_IN) {
             [[maybe_unused]] uint32_t in[16];
             [[maybe_unused]] float v2[32];
             if constexpr (CHUNK_IN) {

@@ -48,6 +48,13 @@ struct epi_chunk_in : std::false_type {};
 template <class E>
 struct epi_chunk_in<E, std::void_t<decltype(E::kChunkIn)>> : std::bool_constant<E::kChunkIn> {};
 
+// Epi::kTransposed: the accumulator tile is the TRANSPOSE of the stored output (rows of the accumulator = columns
+// of the output tensor); input chunks and stores use swapped coordinates and the functor moves the data itself
+template <class E, class = void>
+struct epi_transposed : std::false_type {};
+template <class E>
+struct epi_transposed<E, std::void_t<decltype(E::kTransposed)>> : std::bool_constant<E::kTransposed> {};
+
 // Epi::Side (optional): per-chunk side data that `Side pre(b, m, n)` loads ahead of time and chunk() consumes
 template <class E, class = void>
 struct epi_has_side : std::false_type {};

@@ -30,6 +30,7 @@
 namespace clipk {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static int env_int(const char* name, int dflt);
 constexpr int kDthSplits = 6;   // split-K slabs of the text-gradient accumulator
 
 // rn[row] = 1 / max(||x_row||, 1e-12)      (F.normalize denominator, pacl.py:122,125)
@@ -590,19 +591,37 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
       CLIPK_TRY(launch_nd<epi::Store<false>, false>((engine2_mask() & kK5) != 0, &a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
     }
-    // K6: dV_i = A_i^T Gn_i + E_i^T T^ - rnV^2 dsdot V
+    // K6: dV_i = A_i^T Gn_i + E_i^T T^ - rnV^2 dsdot V.  Computed in whichever orientation wastes less of the
+    // 256-row CTA-pair tiles: rows = patches (P) or, transposed, rows = features (D).
     {
-      OperandDesc a[2], b[2];
-      a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = P; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
-      a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
-      a[0].reverse = 1;
-      b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
-      b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
-      a[1] = a[0]; a[1].ptr = w.E;
-      b[1].ptr = sh.That; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
+      const bool transposed = (engine2_mask() & kK6) != 0 && env_int("CLIPK_AP_K6T", 1) != 0 && D % 8 == 0 &&
+                              (int64_t)round_up(D, 256) * round_up(P, 16) < (int64_t)round_up(P, 256) * round_up(D, 16);
       const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
-      epi::DvOut::Params ep{{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi}, V0, rnV0, dsdot0, P, D};
-      CLIPK_TRY(launch_nd<epi::DvOut, true>((engine2_mask() & kK6) != 0, a, b, 2, ks, ks, P, D, gi, ep, ls));
+      if (transposed) {
+        OperandDesc a[2], b[2];
+        a[0].ptr = w.G; a[0].mn_major = true; a[0].rows = D; a[0].k = Bt; a[0].ld = D; a[0].batch = gi;
+        a[0].batch_stride = (int64_t)Bt * D; a[0].bmul = 1;
+        a[0].reverse = 1;
+        b[0].ptr = w.A; b[0].mn_major = true; b[0].rows = P; b[0].k = Bt; b[0].ld = Ppad; b[0].batch = gi;
+        b[0].batch_stride = (int64_t)Bt * Ppad; b[0].bmul = 1;
+        a[1].ptr = sh.That; a[1].mn_major = true; a[1].rows = D; a[1].k = Bt; a[1].ld = D; a[1].batch = 1; a[1].bmul = 0;
+        b[1] = b[0]; b[1].ptr = w.E;
+        const eng::OutDesc odv{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi};
+        const eng::OutDesc ov{const_cast<__nv_bfloat16*>(V0), D, (int64_t)P * D, P, D, gi};
+        epi::DvOutT::Params ep{odv, ov, rnV0, dsdot0, P};
+        CLIPK_TRY((launch_gemm2<256, true, true, epi::DvOutT>(a, b, 2, ks, ks, D, P, gi, ep, ls)));
+      } else {
+        OperandDesc a[2], b[2];
+        a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = P; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
+        a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
+        a[0].reverse = 1;
+        b[0].ptr = w.G; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
+        b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
+        a[1] = a[0]; a[1].ptr = w.E;
+        b[1].ptr = sh.That; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
+        epi::DvOut::Params ep{{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi}, V0, rnV0, dsdot0, P, D};
+        CLIPK_TRY(launch_nd<epi::DvOut, true>((engine2_mask() & kK6) != 0, a, b, 2, ks, ks, P, D, gi, ep, ls));
+      }
     }
   }
   if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));

@@ -278,6 +278,14 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t cta_mask)
                "h"(cta_mask)
                : "memory");
 }
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+  uint16_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
