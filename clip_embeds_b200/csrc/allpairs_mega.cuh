@@ -22,6 +22,9 @@
 //   backward:  ACTS  A, X = <t^, V>      GNEG  Gn = -beta A V_i      DS   d = Gn V_i^T, X -> E (in place), dsdot
 //              DT    dt^ += E V  (red.add.v4.f32; K folds the images of the group)      DV   dV_i = A^T Gn + E^T T^ - ...
 #pragma once
+#ifndef CLIPK_MEGA_PROF
+#define CLIPK_MEGA_PROF 0
+#endif
 #include "epilogues.cuh"
 #include "gemm2_engine.cuh"
 
@@ -69,6 +72,7 @@ struct Sched {
   int dep_same[kMaxPhases];             // index (into ph[]) of the phase of the SAME group this phase reads, or -1
   int dep_ring[kMaxPhases][2];          // phases of group g - slots that must be complete before this phase writes
   int dt_spb;        // DT: images per K split
+  unsigned need_full[kMaxPhases], need_last[kMaxPhases];   // completion count of a phase: full group / last (short) group
   int total_tiles;
   unsigned* done;    // [ngroups][nph] finished (tile, epilogue warp) counts
   // tensors the epilogues touch
@@ -178,16 +182,33 @@ __device__ __forceinline__ void wait_count(const unsigned* p, unsigned need) {
 // block until everything job (phi, g) reads or overwrites is complete
 __device__ __forceinline__ void wait_deps(const Sched& s, int phi, int g) {
   if (s.flags & 2) return;
+  // one publication per CTA per tile: a job is complete at 2 x its tile count
   const int d = s.dep_same[phi];
-  if (d >= 0) wait_count(s.done + (size_t)g * s.nph + d, (unsigned)job_tiles(s, d, g) * 2u * kEpiWarps);
+  if (d >= 0) wait_count(s.done + (size_t)g * s.nph + d, g == s.ngroups - 1 ? s.need_last[d] : s.need_full[d]);
   const int gp = g - s.slots;
   if (gp >= 0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = s.dep_ring[phi][i];
-      if (r >= 0) wait_count(s.done + (size_t)gp * s.nph + r, (unsigned)job_tiles(s, r, gp) * 2u * kEpiWarps);
+      if (r >= 0) wait_count(s.done + (size_t)gp * s.nph + r, s.need_full[r]);   // gp is never the last group
     }
   }
+}
+
+// one poll of every dependency of job (phi, g): true when none of them would block
+__device__ __forceinline__ bool deps_ready(const Sched& s, int phi, int g) {
+  if (s.flags & 2) return true;
+  const int d = s.dep_same[phi];
+  if (d >= 0 && ld_acquire(s.done + (size_t)g * s.nph + d) < (g == s.ngroups - 1 ? s.need_last[d] : s.need_full[d])) return false;
+  const int gp = g - s.slots;
+  if (gp >= 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = s.dep_ring[phi][i];
+      if (r >= 0 && ld_acquire(s.done + (size_t)gp * s.nph + r) < s.need_full[r]) return false;
+    }
+  }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------ DT epilogue
@@ -308,17 +329,28 @@ struct EpiCtx {                   // state of one epilogue warp that persists ac
   int slab;                       // chunks staged so far (staging buffer = slab & 1)
   int inq;                        // input chunks requested so far (in buffer = inq & 1)
   unsigned* pending;              // completion counter of the previous tile, published once its stores are complete
+  int pending_g;                  // its group
+  int pending_par;                // tile number & 3 (selects the CTA-level arrival counter: a warp that flushes can be
+                                  // two tiles ahead of the slowest warp of its CTA, so two counters are not enough)
+  unsigned* tile_done;            // [4] shared-memory arrival counters of the 8 epilogue warps
   long long pfc[8], pfn[8], pfw[8];   // per phase: cycles in chunks, chunk count, cycles in the TMA-store wait
   long long pfq[4];
   long long pf[6];                // diagnostics (flags & 4): cycles in dep wait / tfull wait / chunks / first-chunk publish
 };
 
 // lane 0 only; everything this warp wrote for that tile is complete
-__device__ __forceinline__ void publish_f(int flags, unsigned* ctr) {
-  if (!(flags & 1)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+// The last of the 8 epilogue warps to get here publishes the tile for the whole CTA: one gpu-scope fence and one
+// global reduction per CTA and tile instead of eight.  (cta-scope fence + shared-memory arrival: the publisher's
+// gpu-scope fence is cumulative over what the other warps wrote before they arrived.)
+__device__ __forceinline__ void publish_f(int flags, unsigned* ctr, unsigned* tile_done_slot) {
+  __threadfence_block();
+  const unsigned old = atomicAdd(tile_done_slot, 1u);
+  if (old == kEpiWarps - 1) {
+    *tile_done_slot = 0u;
+    if (!(flags & 1)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+  }
 }
-__device__ __forceinline__ void publish(const Sched& s, unsigned* ctr) { publish_f(s.flags, ctr); }
 __device__ __forceinline__ void stage_rows(uint8_t* wbuf, const float* v, int lane, uint32_t sw) {
   const uint32_t rowbase = ptx::smem_u32(wbuf) + lane * 64;
 #pragma unroll
@@ -340,7 +372,7 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
   constexpr bool TMA_OUT2 = eng::epi_tma_out2<Epi>::value;
   constexpr bool CHUNK_IN = eng::epi_chunk_in<Epi>::value;
   constexpr bool HAS_SIDE = eng::epi_has_side<Epi>::value;
-  const long long pf_e = clock64();
+  [[maybe_unused]] const long long pf_e = CLIPK_MEGA_PROF ? clock64() : 0;
   // Everything the chunk loop touches is copied into local values first: `cx`, `s` and the tile live in memory, and
   // every asm volatile with a "memory" clobber (mbarrier waits, shared stores, fences, TMA) would otherwise force
   // them to be re-loaded, which serialises the chunk math.
@@ -350,6 +382,7 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
   const uint32_t sw = cx.sw;
   int slab = cx.slab, inq = cx.inq;
   unsigned* pending = cx.pending;
+  unsigned* const pending_slot = cx.tile_done + cx.pending_par;
   uint8_t* const c_out = cx.out_smem + ew * 2 * kChunkBytes;
   uint8_t* const c_out2 = cx.out2_smem + ew * 2 * kChunkBytes;
   uint8_t* const c_in = cx.in_smem + ew * 2 * kChunkBytes;
@@ -385,11 +418,11 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
   epi.tile_begin(b, m, x.n0);
   if constexpr (HAS_SIDE) side = epi.pre(b, m, x.n0 + half * 32);
   issue_in(x.n0 + half * 32);
-  const long long pf_a = clock64();
-  if (flags & 4) cx.pfq[2] += pf_a - pf_e;
+  [[maybe_unused]] const long long pf_a = CLIPK_MEGA_PROF ? clock64() : 0;
+  if (CLIPK_MEGA_PROF && (flags & 4)) cx.pfq[2] += pf_a - pf_e;
   ptx::mbar_wait(&c_tfull[buf], bphase);
   ptx::tc_fence_after();
-  const long long pf_b = clock64();
+  [[maybe_unused]] const long long pf_b = CLIPK_MEGA_PROF ? clock64() : 0;
   const uint32_t tacc = c_tmem + (static_cast<uint32_t>(q4 * 32) << 16) + buf * 256;
   auto release_tmem = [&]() {
     ptx::tc_fence_before();
@@ -437,11 +470,11 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
         ptx::bulk_commit_group();
         if (pending != nullptr) {                // the previous tile's stores: all but this group are complete
           ptx::bulk_wait_group<1>();
-          publish_f(flags, pending);
+          publish_f(flags, pending, pending_slot);
         } else {
-          const long long pf_c = clock64();
+          [[maybe_unused]] const long long pf_c = CLIPK_MEGA_PROF ? clock64() : 0;
           ptx::bulk_wait_group_read<1>();
-          pf_w += clock64() - pf_c;
+          if (CLIPK_MEGA_PROF) pf_w += clock64() - pf_c;
         }
       }
       pending = nullptr;
@@ -451,7 +484,7 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
       if (pending != nullptr) {                  // (warp-uniform) no store in this phase: drain and publish now
         if (lane == 0) {
           ptx::bulk_wait_group<0>();
-          publish_f(flags, pending);
+          publish_f(flags, pending, pending_slot);
         }
         pending = nullptr;
         __syncwarp();
@@ -486,7 +519,7 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
   }
   epi.tile_end(b, m, x.n0, x.tn_idx, half);
   __syncwarp();
-  if (flags & 4) {
+  if (CLIPK_MEGA_PROF && (flags & 4)) {
     cx.pf[1] += pf_b - pf_a;
     cx.pf[2] += clock64() - pf_b;
     cx.pf[3] += jmax;
@@ -497,6 +530,8 @@ __device__ __forceinline__ void run_tile(EpiCtx& cx, const Tile xt) {
   cx.slab = slab;
   cx.inq = inq;
   cx.pending = my_counter;
+  cx.pending_g = xt.g;
+  cx.pending_par = c_it & 3;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -510,16 +545,18 @@ struct Pipe {            // per-role ring / accumulator state that persists acro
 // own register allocation (as in the stand-alone engine), the call happens once per job and the persistent state
 // travels through `cx`.
 template <int PH>
-__device__ __noinline__ int run_job(EpiCtx& cx, const Cursor& cur, int t, int rank, int num_clusters) {
+__device__ __forceinline__ int run_job(EpiCtx& cx, const Cursor& cur, int t, int rank, int num_clusters) {
   const Sched& s = *cx.s;
   const int job_end = cur.job_begin + cur.job_n;
   for (; t < job_end; t += num_clusters) {
-    const long long q0 = clock64();
+    [[maybe_unused]] const long long q0 = CLIPK_MEGA_PROF ? clock64() : 0;
     const Tile x = decode(s, cur, t, rank);
-    const long long q1 = clock64();
+    [[maybe_unused]] const long long q1 = CLIPK_MEGA_PROF ? clock64() : 0;
     run_tile<PH>(cx, x);
-    cx.pfq[0] += q1 - q0;
-    cx.pfq[1] += clock64() - q1;
+    if (CLIPK_MEGA_PROF) {
+      cx.pfq[0] += q1 - q0;
+      cx.pfq[1] += clock64() - q1;
+    }
     ++cx.it;
   }
   return t;
@@ -527,7 +564,8 @@ __device__ __noinline__ int run_job(EpiCtx& cx, const Cursor& cur, int t, int ra
 
 // The three warp roles are separate, non-inlined functions: each gets its own register allocation (the TMA producer
 // and the MMA issuer are single latency-critical threads and must not inherit the epilogue's spills).
-__device__ __noinline__ void producer_role(const Maps& maps, const Sched& s, uint8_t* smem, uint64_t* full_bar,
+template <bool BWD>
+__device__ __forceinline__ void producer_role(const Maps& maps, const Sched& s, uint8_t* smem, uint64_t* full_bar,
                                            uint64_t* empty_bar, int rank, int cluster_id, int num_clusters) {
   const bool leader = rank == 0;
     if (ptx::elect_one()) {
@@ -616,7 +654,7 @@ __device__ __noinline__ void producer_role(const Maps& maps, const Sched& s, uin
     }
 }
 
-__device__ __noinline__ void mma_role(const Sched& s, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+__device__ __forceinline__ void mma_role(const Sched& s, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
                                       uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base, int cluster_id,
                                       int num_clusters) {
   const bool leader = true;
@@ -662,7 +700,8 @@ __device__ __noinline__ void mma_role(const Sched& s, uint8_t* smem, uint64_t* f
     }
 }
 
-__device__ __noinline__ void epilogue_role(const Maps& maps, const Sched& s, uint8_t* out_smem, uint8_t* out2_smem,
+template <bool BWD>
+__device__ __forceinline__ void epilogue_role(const Maps& maps, const Sched& s, uint8_t* out_smem, uint8_t* out2_smem,
                                            uint8_t* in_smem, uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* in_bar,
                                            uint32_t tmem_base, int rank, int cluster_id, int num_clusters) {
   const int warp = threadIdx.x >> 5;
@@ -684,58 +723,69 @@ __device__ __noinline__ void epilogue_role(const Maps& maps, const Sched& s, uin
     cx.tempty_leader[0] = tempty_leader[0]; cx.tempty_leader[1] = tempty_leader[1];
     cx.tmem_base = tmem_base;
     cx.q4 = q4; cx.ew = ew; cx.half = half; cx.lane = lane; cx.sw = sw;
-    cx.it = 0; cx.slab = 0; cx.inq = 0; cx.pending = nullptr;
+    cx.it = 0; cx.slab = 0; cx.inq = 0; cx.pending = nullptr; cx.pending_g = -1; cx.pending_par = 0;
+    cx.tile_done = reinterpret_cast<unsigned*>(in_bar + 2 * kEpiWarps);
     for (int i = 0; i < 6; ++i) cx.pf[i] = 0;
     for (int i = 0; i < 4; ++i) cx.pfq[i] = 0;
     for (int i = 0; i < 8; ++i) cx.pfc[i] = cx.pfn[i] = cx.pfw[i] = 0;
-    const long long pf_start = clock64();
+    [[maybe_unused]] const long long pf_start = CLIPK_MEGA_PROF ? clock64() : 0;
 
     for (int t = cluster_id; t < s.total_tiles;) {
       cur.seek(s, t);
       if (cur.job_begin != checked_job) {     // the epilogue reads in-kernel products too (X chunks, dsdot)
-        const long long pf_d = clock64();
-        ++cx.pf[5];
-        // publish the previous tile first: what this job waits for may (transitively) be that very tile
-        if (cx.pending != nullptr) {
-          if (lane == 0) {
-            ptx::bulk_wait_group<0>();
-            publish(s, cx.pending);
+        [[maybe_unused]] const long long pf_d = CLIPK_MEGA_PROF ? clock64() : 0;
+        if (CLIPK_MEGA_PROF) ++cx.pf[5];
+        // Never block with an unpublished tile: whatever this job waits for may, through other CTA pairs that are
+        // themselves waiting, depend on it.  When the dependencies are already complete (the common case) nothing is
+        // flushed and the tile is published, as usual, behind the first chunk of the next tile.
+        if (lane == 0) ptx::bulk_wait_group_read<0>();   // [out2 | in] staging is shared between phases
+        const bool ready = __shfl_sync(0xffffffffu, lane == 0 ? (deps_ready(s, cur.phi, cur.g) ? 1 : 0) : 0, 0) != 0;
+        if (!ready) {
+          if (cx.pending != nullptr) {
+            if (lane == 0) {
+              ptx::bulk_wait_group<0>();
+              publish_f(s.flags, cx.pending, cx.tile_done + cx.pending_par);
+            }
+            cx.pending = nullptr;
           }
-          cx.pending = nullptr;
+          if (lane == 0) wait_deps(s, cur.phi, cur.g);
         }
-        if (lane == 0) wait_deps(s, cur.phi, cur.g);
         __syncwarp();
         ptx::fence_proxy_async_all();
         checked_job = cur.job_begin;
-        cx.pf[0] += clock64() - pf_d;
+        if (CLIPK_MEGA_PROF) cx.pf[0] += clock64() - pf_d;
       }
-      switch (s.ph[cur.phi]) {
-        case PH_ACT: t = run_job<PH_ACT>(cx, cur, t, rank, num_clusters); break;
-        case PH_USQ: t = run_job<PH_USQ>(cx, cur, t, rank, num_clusters); break;
-        case PH_ACTS: t = run_job<PH_ACTS>(cx, cur, t, rank, num_clusters); break;
-        case PH_GNEG: t = run_job<PH_GNEG>(cx, cur, t, rank, num_clusters); break;
-        case PH_DS: t = run_job<PH_DS>(cx, cur, t, rank, num_clusters); break;
-        case PH_DT: t = run_job<PH_DT>(cx, cur, t, rank, num_clusters); break;
-        default: t = run_job<PH_DV>(cx, cur, t, rank, num_clusters); break;
+      if constexpr (!BWD) {
+        if (s.ph[cur.phi] == PH_ACT) t = run_job<PH_ACT>(cx, cur, t, rank, num_clusters);
+        else t = run_job<PH_USQ>(cx, cur, t, rank, num_clusters);
+      } else {
+        switch (s.ph[cur.phi]) {
+          case PH_ACTS: t = run_job<PH_ACTS>(cx, cur, t, rank, num_clusters); break;
+          case PH_GNEG: t = run_job<PH_GNEG>(cx, cur, t, rank, num_clusters); break;
+          case PH_DS: t = run_job<PH_DS>(cx, cur, t, rank, num_clusters); break;
+          case PH_DT: t = run_job<PH_DT>(cx, cur, t, rank, num_clusters); break;
+          default: t = run_job<PH_DV>(cx, cur, t, rank, num_clusters); break;
+        }
       }
     }
     if (lane == 0) {
       ptx::bulk_wait_group<0>();
-      if (cx.pending != nullptr) publish(s, cx.pending);
+      if (cx.pending != nullptr) publish_f(s.flags, cx.pending, cx.tile_done + cx.pending_par);
     }
-    if ((s.flags & 4) && lane == 0 && (blockIdx.x == 2 || blockIdx.x == 77) && (warp == kEpiWarp0 || warp == kEpiWarp0 + 5))
+    if (CLIPK_MEGA_PROF && (s.flags & 4) && lane == 0 && (blockIdx.x == 2 || blockIdx.x == 77) && (warp == kEpiWarp0 || warp == kEpiWarp0 + 5))
       printf("mega prof blk %d warp %d: tiles %d total %lld cyc | jobchg %lld (%lld cyc) tfull-wait %lld  chunks %lld (%lld chunks) "
              "publish-in-chunk %lld\n", blockIdx.x, warp, cx.it, clock64() - pf_start, cx.pf[5], cx.pf[0], cx.pf[1], cx.pf[2],
              cx.pf[3], cx.pf[4]);
-    if ((s.flags & 4) && lane == 0 && blockIdx.x == 2 && warp == kEpiWarp0)
+    if (CLIPK_MEGA_PROF && (s.flags & 4) && lane == 0 && blockIdx.x == 2 && warp == kEpiWarp0)
       printf("   decode %lld  run_tile %lld  (entry->tfull-wait %lld)\n", cx.pfq[0], cx.pfq[1], cx.pfq[2]);
-    if ((s.flags & 4) && lane == 0 && blockIdx.x == 2 && warp == kEpiWarp0)
+    if (CLIPK_MEGA_PROF && (s.flags & 4) && lane == 0 && blockIdx.x == 2 && warp == kEpiWarp0)
       for (int i = 0; i < 7; ++i)
         if (cx.pfn[i] > 0)
           printf("   phase %d: %lld chunks, %lld cyc/chunk, of which store-read wait %lld\n", i, cx.pfn[i], cx.pfc[i] / cx.pfn[i],
                  cx.pfw[i] / cx.pfn[i]);
   }
 
+template <bool BWD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 allpairs_mega_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Sched s_param) {
   // The role functions read the schedule through a pointer: keep it in shared memory (a generic load from the
@@ -776,6 +826,7 @@ allpairs_mega_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
       ptx::mbar_init(&tempty_bar[i], 2 * kEpiWarps);
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) ptx::mbar_init(&in_bar[i], 1);
+    for (int i = 0; i < 4; ++i) reinterpret_cast<unsigned*>(in_bar + 2 * kEpiWarps)[i] = 0u;   // CTA-level tile arrival counters
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -788,11 +839,11 @@ allpairs_mega_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    producer_role(maps, s, smem, full_bar, empty_bar, rank, cluster_id, num_clusters);
+    producer_role<BWD>(maps, s, smem, full_bar, empty_bar, rank, cluster_id, num_clusters);
   } else if (warp == 1) {
     if (leader) mma_role(s, smem, full_bar, empty_bar, tfull_bar, tempty_bar, tmem_base, cluster_id, num_clusters);
   } else if (warp >= kEpiWarp0) {
-    epilogue_role(maps, s, out_smem, out2_smem, in_smem, tfull_bar, tempty_bar, in_bar, tmem_base, rank, cluster_id,
+    epilogue_role<BWD>(maps, s, out_smem, out2_smem, in_smem, tfull_bar, tempty_bar, in_bar, tmem_base, rank, cluster_id,
                   num_clusters);
   }
 

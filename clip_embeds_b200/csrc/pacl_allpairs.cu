@@ -375,6 +375,10 @@ static int mega_launch(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, i
     for (int i = 0; i < sc.nph; ++i) total += mega::job_tiles(sc, i, g);
   CLIPK_REQUIRE(total < 0x3fffffff, "pacl_allpairs: tile sequence too long (%lld)", total);
   sc.total_tiles = (int)total;
+  for (int i = 0; i < sc.nph; ++i) {
+    sc.need_full[i] = 2u * (unsigned)mega::job_tiles(sc, i, 0);
+    sc.need_last[i] = 2u * (unsigned)mega::job_tiles(sc, i, pl.ngroups - 1);
+  }
   sc.done = w.done;
   sc.rnV = rnV; sc.rnT = rnT; sc.num = num; sc.usq = usq;
   sc.alpha = w.alpha; sc.beta = w.beta; sc.dsdot = w.dsdot; sc.dth = w.dth;
@@ -385,7 +389,9 @@ static int mega_launch(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, i
   int dev = 0;
   CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
   if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
-    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(mega::allpairs_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(mega::allpairs_mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          mega::kSmemTotal));
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(mega::allpairs_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           mega::kSmemTotal));
     attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
@@ -393,7 +399,8 @@ static int mega_launch(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, i
   const int grid = 2 * (sc.total_tiles < pairs ? sc.total_tiles : pairs);
   const bool tr = trace_enabled();
   if (tr) trace_begin(backward ? "allpairs_mega_kernel (backward)" : "allpairs_mega_kernel (forward)", st);
-  mega::allpairs_mega_kernel<<<grid, mega::kThreads, mega::kSmemTotal, st>>>(mp, sc);
+  if (backward) mega::allpairs_mega_kernel<true><<<grid, mega::kThreads, mega::kSmemTotal, st>>>(mp, sc);
+  else mega::allpairs_mega_kernel<false><<<grid, mega::kThreads, mega::kSmemTotal, st>>>(mp, sc);
   if (tr) trace_end(st);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());

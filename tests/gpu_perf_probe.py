@@ -86,7 +86,8 @@ if __name__ == "__main__":
         for grp in groups:
             allpairs(B, 576, 768, grp)
     if cmd == "once":
-        allpairs_once(int(sys.argv[2]), 576, 768, int(sys.argv[3]))
+        a = sys.argv[3]
+        allpairs_once(int(sys.argv[2]), 576, 768, tuple(int(y) for y in a.split(":")) if ":" in a else int(a))
     if cmd == "tile":
         gemm(1024, 576, 768, nb=64)
         gemm(1024, 576, 6144, nb=8)
