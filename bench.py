@@ -297,7 +297,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": world * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "eng::gemm_kernel (tcgen05 engine, all fused-epilogue instantiations of one step)",
+                         "traffic": None, "kernel": "eng2::gemm2_kernel (tcgen05 cta_group::2 engine, all fused-epilogue instantiations of one step)",
                          "algorithmic_flops_per_step_per_gpu": flops_per_rank, "engine_ms_per_step": eng_ms,
                          "peak_source": peak_src},
             "clocks": clocks,

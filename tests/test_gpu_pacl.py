@@ -105,6 +105,25 @@ def test_allpairs_groups_and_ones():
     assert max(e3) < 3e-2
 
 
+@pytest.mark.parametrize("sched", [(-4, 2), (-3, 3), (-16, 1), 0])
+def test_allpairs_persistent_kernel(sched):
+    """The dependency-driven persistent kernel (group <= 0: -group images per group, `lanes` groups in lock-step; 0 =
+    automatic): ragged last group, more groups than scratch slots, N tails."""
+    e1 = _allpairs_case(11, 130, 196, 512, seed=51, group=sched)
+    assert e1[0] < 2e-2 and e1[1] < 3e-2 and e1[2] < 3e-2
+    e2 = _allpairs_case(7, 40, 100, 128, seed=41, group=sched, activation="ones")
+    assert max(e2) < 3e-2
+
+
+def test_allpairs_dv_orientations(monkeypatch):
+    """dV GEMM with rows = patches (CLIPK_AP_K6T=0) and transposed, rows = features (default where it wastes less)."""
+    monkeypatch.setenv("CLIPK_AP_K6T", "0")
+    e0 = _allpairs_case(5, 130, 576, 768, seed=31)
+    monkeypatch.setenv("CLIPK_AP_K6T", "1")
+    e1 = _allpairs_case(5, 130, 576, 768, seed=31)
+    assert e0[1] < 3e-2 and e1[1] < 3e-2 and e0[2] < 3e-2 and e1[2] < 3e-2
+
+
 def test_allpairs_loss_golden(goldens):
     """Reference golden G6 (fp32 reference on fp32 inputs) vs the bf16 tensor-core path: bf16 input rounding is part of
     the error here, hence the looser loss tolerance."""
