@@ -30,6 +30,8 @@ SIGNATURES = {
                                         c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
     "clipk_ce_rows": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "clipk_ce_cols": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "clipk_ce_rowsums": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "clipk_ce_merge": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "clipk_ce_scores_grad": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),
     "clipk_ce_rows_grad": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "clipk_sgemm_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_f32,

@@ -97,6 +97,54 @@ __global__ void ce_rows_grad_kernel(const float* __restrict__ L, int M, int N, i
   dL[idx] = wi == 0.f ? 0.f : wi * (expf(L[(int64_t)i * ld + k] - row_lse[i]) - ((int64_t)k == lab ? 1.f : 0.f));
 }
 
+// out2[0] = sum_i row_loss_i,  out2[1] = sum_i (row_lse_i - row_loss_i) = sum of the label logits (the local diagonal)
+__global__ void ce_rowsums_kernel(const float* __restrict__ row_lse, const float* __restrict__ row_loss, int M,
+                                  float* __restrict__ out2) {
+  __shared__ float red[32];
+  float a = 0.f, d = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    a += row_loss[i];
+    d += row_lse[i] - row_loss[i];
+  }
+  a = simt::block_sum(a, red);
+  d = simt::block_sum(d, red);
+  if (threadIdx.x == 0) {
+    out2[0] = a;
+    out2[1] = d;
+  }
+}
+
+// Merge of the per-rank payloads [W][2N + 2] = (col_max [N], col_sum [N], sum row_loss, sum diag):
+//   col_lse[k] = log sum_r col_sum[r][k] exp(col_max[r][k] - max_r)  + max_r        (online-softmax merge)
+//   loss = 0.5 / N * ( sum_r rowloss_r + sum_k col_lse[k] - sum_r diag_r )           (pacl.py:509-512 on the scores)
+__global__ void ce_merge_kernel(const float* __restrict__ g, int W, int N, float* __restrict__ col_lse,
+                                float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int64_t stride = 2 * (int64_t)N + 2;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float mx = -INFINITY;
+    for (int r = 0; r < W; ++r) mx = fmaxf(mx, g[r * stride + k]);
+    float sm = 0.f;
+    for (int r = 0; r < W; ++r) {
+      const float m = g[r * stride + k];
+      if (m > -INFINITY) sm += g[r * stride + N + k] * expf(m - mx);
+    }
+    const float l = mx + logf(sm);
+    col_lse[k] = l;
+    acc += l;
+  }
+  acc = simt::block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    float rl = 0.f, dg = 0.f;
+    for (int r = 0; r < W; ++r) {
+      rl += g[r * stride + 2 * (int64_t)N];
+      dg += g[r * stride + 2 * (int64_t)N + 1];
+    }
+    *loss = 0.5f / (float)N * (rl + acc - dg);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ (2) fp32 GEMM
 // C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + beta * C[m*ldc + n]; 64x64 tile, 4x4 per thread.
 __global__ void __launch_bounds__(256)
@@ -369,6 +417,24 @@ int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, floa
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_cols: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
   clipk::ce_cols_kernel<<<(N + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, col_max, col_sum);
+  clipk::count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_ce_rowsums(const float* row_lse, const float* row_loss, int M, float* out2, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(M > 0, "ce_rowsums: empty input");
+  clipk::ce_rowsums_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_lse, row_loss, M, out2);
+  clipk::count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clipk_ce_merge(const float* gathered, int W, int N, float* col_lse, float* loss, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(W > 0 && N > 0, "ce_merge: empty input");
+  clipk::ce_merge_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(gathered, W, N, col_lse, loss);
   clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;

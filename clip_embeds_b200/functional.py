@@ -180,21 +180,6 @@ def pacl_scores(visual_proj, text_proj, c=1.0, activation="sigmoid", group=None)
 
 
 # --------------------------------------------------------------------------------------------- CE on a score matrix
-def _merge_cols(col_max, col_sum, group=None):
-    """(max, sumexp) partial column statistics -> column LSE, merged across ranks when a group is given."""
-    if group is not None:
-        import torch.distributed as dist
-        W = dist.get_world_size(group)
-        both = torch.stack([col_max, col_sum])                          # [2, N]
-        gathered = [torch.empty_like(both) for _ in range(W)]
-        dist.all_gather(gathered, both, group=group)
-        allb = torch.stack(gathered)                                    # [W, 2, N]
-        gmax = allb[:, 0].max(dim=0).values
-        gsum = (allb[:, 1] * torch.exp(allb[:, 0] - gmax)).sum(dim=0)
-        return gmax + torch.log(gsum)
-    return col_max + torch.log(col_sum)
-
-
 def _k_ce_rows(L, offset):
     """row_lse [M], row_loss [M] of a fp32 matrix (label of row i = i + offset)."""
     M, N = L.shape
@@ -209,6 +194,22 @@ def _k_ce_cols(L):
     col_max, col_sum = _f32(N, device=L.device), _f32(N, device=L.device)
     _lib.call("clipk_ce_cols", L.data_ptr(), M, N, N, col_max.data_ptr(), col_sum.data_ptr(), _stream())
     return col_max, col_sum
+
+
+def _k_ce_payload(L, row_lse, row_loss):
+    """[2N + 2] = (per-column max [N], per-column sum exp(L - max) [N], sum row_loss, sum label logits)."""
+    M, N = L.shape
+    payload = _f32(2 * N + 2, device=L.device)
+    _lib.call("clipk_ce_cols", L.data_ptr(), M, N, N, payload.data_ptr(), payload.data_ptr() + 4 * N, _stream())
+    _lib.call("clipk_ce_rowsums", row_lse.data_ptr(), row_loss.data_ptr(), M, payload.data_ptr() + 8 * N, _stream())
+    return payload
+
+
+def _k_ce_merge(gathered, W, N):
+    """(col_lse [N], global loss [1]) from the W gathered payloads."""
+    col_lse, loss = _f32(N, device=gathered.device), _f32(1, device=gathered.device)
+    _lib.call("clipk_ce_merge", gathered.data_ptr(), W, N, col_lse.data_ptr(), loss.data_ptr(), _stream())
+    return col_lse, loss
 
 
 def _k_ce_scores_grad(L, row_lse, col_lse, offset, w_row, w_col):
@@ -229,18 +230,26 @@ class _ScoreInfoNCE(torch.autograd.Function):
     def forward(ctx, L, offset, group):
         L = L.float().contiguous()
         M, N = L.shape
+        dev = L.device
         row_lse, row_loss = _k_ce_rows(L, offset)
-        col_max, col_sum = _k_ce_cols(L)
-        col_lse = _merge_cols(col_max, col_sum, group)
-        diag = row_lse - row_loss                                        # L[i, i + offset]
-        part = torch.stack([row_loss.sum(), (col_lse[offset:offset + M] - diag).sum()])
+        # payload of this rank: (col_max [N], col_sum [N], sum row_loss, sum label logits) -- ONE all-gather carries the
+        # column statistics and both loss partials
+        payload = _k_ce_payload(L, row_lse, row_loss)
+        W = 1
+        gathered = payload
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(part, group=group)
-        loss = 0.5 * (part[0] + part[1]) / N
-        dL = _k_ce_scores_grad(L, row_lse, col_lse.contiguous(), offset, 0.5 / N, 0.5 / N)
+            W = dist.get_world_size(group)
+            if W > 1:
+                gathered = _f32(W * (2 * N + 2), device=dev)
+                if L.is_cuda:
+                    dist.all_gather_into_tensor(gathered, payload, group=group)
+                else:
+                    dist.all_gather(list(gathered.chunk(W)), payload, group=group)
+        col_lse, loss = _k_ce_merge(gathered, W, N)
+        dL = _k_ce_scores_grad(L, row_lse, col_lse, offset, 0.5 / N, 0.5 / N)
         ctx.save_for_backward(dL)
-        return loss
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):

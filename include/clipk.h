@@ -103,6 +103,12 @@ int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P,
 int clipk_ce_rows(const float* L, int M, int N, int64_t ld, const int64_t* labels, int64_t label_offset,
                   float* row_lse, float* row_loss, void* stream);
 int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, float* col_sum, void* stream);
+/* Sharded InfoNCE on a score matrix with ONE collective: every rank all-gathers a payload of 2N + 2 floats
+ * (col_max [N], col_sum [N] from clipk_ce_cols, then clipk_ce_rowsums' two sums); clipk_ce_merge turns the W gathered
+ * payloads [W][2N+2] into the merged column LSEs and the GLOBAL loss 1/2 (CE(L, I) + CE(L^T, I)) (pacl.py:509-512).
+ *   clipk_ce_rowsums: out2[0] = sum_i row_loss_i, out2[1] = sum_i (row_lse_i - row_loss_i)  (the label logits)  */
+int clipk_ce_rowsums(const float* row_lse, const float* row_loss, int M, float* out2, void* stream);
+int clipk_ce_merge(const float* gathered, int W, int N, float* col_lse, float* loss, void* stream);
 int clipk_ce_scores_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const float* col_lse,
                          int64_t label_offset, float w_row, float w_col, float* dL, void* stream);
 int clipk_ce_rows_grad(const float* L, int M, int N, int64_t ld, const float* row_lse, const int64_t* labels,

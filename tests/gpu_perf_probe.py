@@ -63,6 +63,20 @@ def allpairs(B, P, D, group=None):
           f"-> {B / tb * 1e3:.0f} pairs/s, {fl / tb / 1e9:.0f} TFLOP/s algorithmic", flush=True)
 
 
+def allpairs_rect(Bi, Bt, P, D, group):
+    """One rank's share of the sharded step: Bi local images against Bt gathered texts."""
+    V = torch.randn(Bi, P, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    T = torch.randn(Bt, D, device="cuda").to(torch.bfloat16).requires_grad_()
+    g = torch.randn(Bi, Bt, device="cuda") / Bt
+
+    def fb():
+        V.grad = None
+        T.grad = None
+        Fk.pacl_scores(V, T, 10.0, "sigmoid", group).backward(g)
+    tb = timeit(fb, 10, 3)[0]
+    print(f"allpairs Bi={Bi} Bt={Bt} group={group}: fwd+bwd {tb:.3f} ms -> {12.0*Bi*Bt*P*D/tb/1e9:.0f} TFLOP/s algorithmic", flush=True)
+
+
 def allpairs_once(B, P, D, group):
     V = torch.randn(B, P, D, device="cuda").to(torch.bfloat16).requires_grad_()
     T = torch.randn(B, D, device="cuda").to(torch.bfloat16).requires_grad_()
@@ -85,6 +99,10 @@ if __name__ == "__main__":
         groups = [tuple(int(y) for y in x.split(":")) if ":" in x else int(x) for x in sys.argv[3:]] or [16, 32, 64]
         for grp in groups:
             allpairs(B, 576, 768, grp)
+    if cmd == "apx":
+        Bi, Bt = int(sys.argv[2]), int(sys.argv[3])
+        for x in sys.argv[4:]:
+            allpairs_rect(Bi, Bt, 576, 768, tuple(int(y) for y in x.split(":")) if ":" in x else int(x))
     if cmd == "once":
         a = sys.argv[3]
         allpairs_once(int(sys.argv[2]), 576, 768, tuple(int(y) for y in a.split(":")) if ":" in a else int(a))

@@ -48,7 +48,19 @@ def _patch_cpu_kernels():
         hit[torch.arange(L.shape[0]), torch.arange(L.shape[0]) + offset] = 1.0
         return w_row * (torch.exp(L - row_lse[:, None]) - hit) + w_col * (torch.exp(L - col_lse[None, :]) - hit)
 
+    def k_payload(L, row_lse, row_loss):
+        mx, sm = k_cols(L)
+        return torch.cat([mx, sm, row_loss.sum()[None], (row_lse - row_loss).sum()[None]])
+
+    def k_merge(gathered, W, N):
+        g = gathered.reshape(W, 2 * N + 2)
+        gmax = g[:, :N].max(dim=0).values
+        col_lse = gmax + torch.log((g[:, N:2 * N] * torch.exp(g[:, :N] - gmax)).sum(dim=0))
+        loss = 0.5 / N * (g[:, 2 * N].sum() + col_lse.sum() - g[:, 2 * N + 1].sum())
+        return col_lse, loss.reshape(1)
+
     Fk._k_ce_rows, Fk._k_ce_cols, Fk._k_ce_scores_grad = k_rows, k_cols, k_grad
+    Fk._k_ce_payload, Fk._k_ce_merge = k_payload, k_merge
     Fk._need_cuda = lambda *a: None
     Fk.pacl_scores = lambda V, T, c=1.0, activation="sigmoid", group=None: O.pacl_allpairs_scores(V, T, c, activation)
 
