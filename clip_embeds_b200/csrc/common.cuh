@@ -144,7 +144,8 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
   constexpr bool kTmaOut = eng::epi_tma_out<Epi>::value;
   constexpr bool kTmaOut2 = eng::epi_tma_out2<Epi>::value;
   constexpr bool kChunkIn = eng::epi_chunk_in<Epi>::value;
-  using L = eng2::SmemLayout<BN, kDual, kTmaOut, kTmaOut2, kChunkIn>;
+  constexpr int kEpiWarps = eng::epi_warps<Epi>::value;
+  using L = eng2::SmemLayout<BN, kDual, kTmaOut, kTmaOut2, kChunkIn, kEpiWarps>;
   eng::OperandMaps maps;
   memset(&maps, 0, sizeof(maps));
   eng::Problem pb;
@@ -207,7 +208,7 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
   const int grid = 2 * (total < pairs ? total : pairs);
   const bool tr = trace_enabled();
   if (tr) trace_begin(__PRETTY_FUNCTION__, stream);
-  kern<<<grid, eng2::kThreads, L::kTotal, stream>>>(maps, pb, ep);
+  kern<<<grid, eng2::threads_for(kEpiWarps), L::kTotal, stream>>>(maps, pb, ep);
   if (tr) trace_end(stream);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());

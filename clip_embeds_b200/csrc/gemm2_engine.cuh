@@ -39,13 +39,14 @@ using eng::ksteps_of;
 
 constexpr int BM = 128;            // accumulator rows per CTA; a CTA pair computes 2 * BM rows
 constexpr int BK = 64;
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;          // default: 4 control warps + 8 epilogue warps
+constexpr int threads_for(int epi_warps) { return 128 + 32 * epi_warps; }
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiBarId = 1;
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN, bool DUAL = false, bool TMA_OUT = false, bool TMA_OUT2 = false, bool CHUNK_IN = false>
+template <int BN, bool DUAL = false, bool TMA_OUT = false, bool TMA_OUT2 = false, bool CHUNK_IN = false, int kEpiWarps = 8>
 struct SmemLayout {
   static constexpr int kA1Bytes = BM * BK * 2;
   static constexpr int kABytes = kA1Bytes * (DUAL ? 2 : 1);
@@ -93,7 +94,7 @@ __device__ __forceinline__ int tile_ncols(const Problem& pb, int n0) {
 }
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for(eng::epi_warps<Epi>::value), 1)
 gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const typename Epi::Params ep) {
   constexpr bool DUAL = epi_dual<Epi>::value;
   constexpr bool TMA_OUT = epi_tma_out<Epi>::value;
@@ -108,7 +109,10 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   static_assert(!B_MN || (BN % 128 == 0), "MN-major B: each CTA's half must be whole 64-wide swizzle groups");
   static_assert(!DUAL || (BN <= 128 && !A_MN), "dual accumulators: BN <= 128, K-major A operands");
   constexpr int kAccCols = DUAL ? 2 * BN : BN;
-  using L = SmemLayout<BN, DUAL, TMA_OUT, TMA_OUT2, CHUNK_IN>;
+  constexpr int kEpiWarps = eng::epi_warps<Epi>::value;     // shadows the namespace default
+  constexpr int NPH = kEpiWarps / 4;                        // column phases: warp (q4, phase) takes chunks phase, phase + NPH, ...
+  static_assert(kEpiWarps == 8 || kEpiWarps == 12, "8 or 12 epilogue warps");
+  using L = SmemLayout<BN, DUAL, TMA_OUT, TMA_OUT2, CHUNK_IN, kEpiWarps>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -297,15 +301,18 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
       ptx::tc_fence_after();
       PF_MARK(pf_wait)
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * kAccCols;
-      const int jn = (pb.N - n0 + 63) >> 6;
-      const int jmax = jn < BN / 64 ? jn : BN / 64;
+      // chunks (32 columns) of this tile that hold at least one existing column, and this warp's share of them
+      const int nch_all = (pb.N - n0 + 31) >> 5;
+      const int nch = nch_all < BN / 32 ? nch_all : BN / 32;
+      const int jmax_raw = (nch - half + NPH - 1) / NPH;
+      const int jmax = jmax_raw > 0 ? jmax_raw : 1;          // every warp walks at least one chunk (TMA clips it)
       [[maybe_unused]] typename eng::side_of<Epi>::type side_next{};
       // side data / input chunk of the chunk after (tile, j): next chunk of this tile, else the first chunk of this
       // CTA's next tile
       auto prefetch_next = [&](int j) {
         if (j + 1 < jmax) {
-          if constexpr (HAS_SIDE) side_next = epi.pre(b, m, n0 + (2 * (j + 1) + half) * 32);
-          issue_in(slab + 1, b, m0 + q4 * 32, n0 + (2 * (j + 1) + half) * 32);
+          if constexpr (HAS_SIDE) side_next = epi.pre(b, m, n0 + (NPH * (j + 1) + half) * 32);
+          issue_in(slab + 1, b, m0 + q4 * 32, n0 + (NPH * (j + 1) + half) * 32);
         } else if (nx.valid) {
           if constexpr (HAS_SIDE) side_next = epi.pre(nx.b, nx.m0 + q4 * 32 + lane, nx.n0 + half * 32);
           issue_in(slab + 1, nx.b, nx.m0 + q4 * 32, nx.n0 + half * 32);
@@ -355,7 +362,7 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
       if constexpr (DUAL) {
 #pragma unroll 1
         for (int j = 0; j < jmax; ++j) {
-          const int c = 2 * j + half;
+          const int c = NPH * j + half;
           float v[32], v1[32];
           ptx::tmem_ld_32x32(tacc + c * 32, v);
           ptx::tmem_ld_32x32(tacc + BN + c * 32, v1);
@@ -373,7 +380,11 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
       } else {
         // single accumulator: the TMEM load of chunk j+1 is in flight while chunk j is processed (ping-pong registers)
         auto process = [&](float* v, int j) {
-          const int c = 2 * j + half;
+          const int c = NPH * j + half;
+          if (c * 32 >= pb.N - n0) {       // (warp-uniform) chunk past the tile's last column: the MMA never wrote it
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
           prefetch_next(j);
           if constexpr (TRANSPOSED) {
             // the functor reads its input chunk from / writes its output chunk to the staging buffers itself
@@ -424,13 +435,13 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
         for (int j = 0; j < jmax; j += 2) {
           ptx::tmem_ld_wait();
           PF_MARK(pf_ld)
-          if (j + 1 < jmax) ptx::tmem_ld_32x32(tacc + (2 * (j + 1) + half) * 32, vb);
+          if (j + 1 < jmax) ptx::tmem_ld_32x32(tacc + (NPH * (j + 1) + half) * 32, vb);
           else release_tmem();
           process(va, j);
           if (j + 1 < jmax) {
             ptx::tmem_ld_wait();
             PF_MARK(pf_ld)
-            if (j + 2 < jmax) ptx::tmem_ld_32x32(tacc + (2 * (j + 2) + half) * 32, va);
+            if (j + 2 < jmax) ptx::tmem_ld_32x32(tacc + (NPH * (j + 2) + half) * 32, va);
             else release_tmem();
             process(vb, j + 1);
           }

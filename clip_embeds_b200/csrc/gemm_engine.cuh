@@ -55,6 +55,15 @@ struct epi_transposed : std::false_type {};
 template <class E>
 struct epi_transposed<E, std::void_t<decltype(E::kTransposed)>> : std::bool_constant<E::kTransposed> {};
 
+// Epi::kEpiWarps (optional, CTA-pair engine): epilogue warps per CTA, 8 (default) or 12.  Twelve = three warps per
+// SMSP, for latency-bound epilogues whose tiles are 192 columns wide (6 chunks: two per column phase); the register
+// budget drops from 168 to 128 per thread.  (Measured on the all-pairs activation kernels: slower than 8 -- fewer
+// smem stages and serialised math cost more than the extra warps hide -- so nothing selects 12 at present.)
+template <class E, class = void>
+struct epi_warps : std::integral_constant<int, 8> {};
+template <class E>
+struct epi_warps<E, std::void_t<decltype(E::kEpiWarps)>> : std::integral_constant<int, E::kEpiWarps> {};
+
 // Epi::Side (optional): per-chunk side data that `Side pre(b, m, n)` loads ahead of time and chunk() consumes
 template <class E, class = void>
 struct epi_has_side : std::false_type {};
