@@ -365,8 +365,10 @@ static int mega_launch(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, i
     sc.ph[0] = mega::PH_ACTS; sc.tm[0] = tmT; sc.tn[0] = tnP; sc.dep_ring[0][0] = 3; sc.dep_ring[0][1] = 4;
     sc.ph[1] = mega::PH_GNEG; sc.tm[1] = tmT; sc.tn[1] = tnD; sc.dep_same[1] = 0;
     sc.ph[2] = mega::PH_DS; sc.tm[2] = tmT; sc.tn[2] = tnP; sc.dep_same[2] = 1;
-    sc.ph[3] = mega::PH_DT; sc.tm[3] = tmT; sc.tn[3] = tnD; sc.dep_same[3] = 2;
-    sc.ph[4] = mega::PH_DV; sc.tm[4] = tmP; sc.tn[4] = tnD; sc.dep_same[4] = 2;
+    // dV before dT: the dT tiles are long (K folds the images of the group) and nothing in the block depends on them,
+    // so they go last, where the imbalance they cause overlaps the next block's first phase
+    sc.ph[3] = mega::PH_DV; sc.tm[3] = tmP; sc.tn[3] = tnD; sc.dep_same[3] = 2;
+    sc.ph[4] = mega::PH_DT; sc.tm[4] = tmT; sc.tn[4] = tnD; sc.dep_same[4] = 2;
   }
   sc.dt_spb = env_int("CLIPK_MEGA_DTSPB", pl.gs);      // images folded into one DT tile's K range
   if (sc.dt_spb < 1) sc.dt_spb = 1;
