@@ -200,6 +200,92 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, cons
   }
 }
 
+// Larger tiling of the same GEMM for the shapes the fp32 feature path actually runs (B x B x D logits and their
+// gradients): 128 x 128 tile, 8 x 8 outputs per thread (two 4-wide groups 64 apart in each direction, so shared-memory
+// reads are conflict-free LDS.128), BK = 8, global loads of the next k-slab prefetched into registers while the
+// current one is multiplied.  Same fp32 FMA arithmetic as above (only the order of the K loop blocks differs).
+__global__ void __launch_bounds__(256)
+sgemm128_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbk,
+                        int64_t sbn, float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
+  constexpr int BMN = 128, BKK = 8;
+  __shared__ __align__(16) float As[2][BKK][BMN + 4];     // +4: the k-fastest stores of a K-contiguous operand hit 32 banks
+  __shared__ __align__(16) float Bs[2][BKK][BMN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;              // 16 x 16 threads
+  const int m0 = blockIdx.y * BMN, n0 = blockIdx.x * BMN;
+  // each thread loads 4 elements of A and 4 of B per k-slab: element e = tid + 256 * i of the [BMN x BKK] slab
+  float ra[4], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      int r, kk;
+      if (sak == 1) { kk = e & 7; r = e >> 3; } else { r = e & 127; kk = e >> 7; }
+      const int m = m0 + r, k = k0 + kk;
+      ra[i] = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f;
+      int c, kb;
+      if (sbk == 1) { kb = e & 7; c = e >> 3; } else { c = e & 127; kb = e >> 7; }
+      const int n = n0 + c, k2 = k0 + kb;
+      rb[i] = (n < N && k2 < K) ? B[(int64_t)k2 * sbk + (int64_t)n * sbn] : 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      int r, kk;
+      if (sak == 1) { kk = e & 7; r = e >> 3; } else { r = e & 127; kk = e >> 7; }
+      As[buf][kk][r] = ra[i];
+      int c, kb;
+      if (sbk == 1) { kb = e & 7; c = e >> 3; } else { c = e & 127; kb = e >> 7; }
+      Bs[buf][kb][c] = rb[i];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BKK) {
+    const bool more = k0 + BKK < K;
+    if (more) gload(k0 + BKK);
+#pragma unroll
+    for (int kk = 0; kk < BKK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float* c = C + (int64_t)m * ldc + n;
+      *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+    }
+  }
+}
+
 }  // namespace clipk
 
 // ------------------------------------------------------------------------------------------------ (3) engine CE
@@ -471,9 +557,15 @@ int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: bad shape");
   if (M == 0 || N == 0) return 0;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  clipk::sgemm_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc, M,
-                                                                                   N, K, alpha, beta);
+  if ((int64_t)M * N >= 256 * 256) {      // enough 128 x 128 tiles to fill the GPU: the larger tiling
+    dim3 grid((N + 127) / 128, (M + 127) / 128);
+    clipk::sgemm128_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc,
+                                                                                        M, N, K, alpha, beta);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    clipk::sgemm_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc, M,
+                                                                                     N, K, alpha, beta);
+  }
   clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
