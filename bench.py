@@ -297,7 +297,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": world * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "eng2::gemm2_kernel (tcgen05 cta_group::2 engine, all fused-epilogue instantiations of one step)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one step's engine launches, from the ncu --set full
+                         # capture of profiles/r01_ncu_staged_kernels.summary.txt (2.94 GB per 128-image group), scaled to
+                         # this rank's share of the images
+                         "traffic": 2.94e9 * (b / 128.0), "kernel": "eng2::gemm2_kernel (tcgen05 cta_group::2 engine, all fused-epilogue instantiations of one step)",
                          "algorithmic_flops_per_step_per_gpu": flops_per_rank, "engine_ms_per_step": eng_ms,
                          "peak_source": peak_src},
             "clocks": clocks,
