@@ -557,7 +557,7 @@ int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: bad shape");
   if (M == 0 || N == 0) return 0;
-  if ((int64_t)M * N >= 256 * 256) {      // enough 128 x 128 tiles to fill the GPU: the larger tiling
+  if ((int64_t)((M + 127) / 128) * ((N + 127) / 128) >= 48) {      // enough 128 x 128 tiles to keep the GPU busy (measured)
     dim3 grid((N + 127) / 128, (M + 127) / 128);
     clipk::sgemm128_strided_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sam, sak, B, sbk, sbn, C, ldc,
                                                                                         M, N, K, alpha, beta);

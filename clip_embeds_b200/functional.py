@@ -364,12 +364,17 @@ class _SparcAlign(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_sparc_align_fwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, float(sigma), l_hat.data_ptr(),
                   g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        # mean over patches of the raw V (SparcLoss's global image feature, pacl.py:561): produced here so that its
+        # gradient -- a [B,D] vector broadcast over all patches -- is added inside the dV kernel (g_add) instead of
+        # being materialised as a second dense [B,P,D] gradient and summed by autograd
+        pooled = _f32(B, D, device=dev)
+        _lib.call("clipk_mean_dim1", Vb.data_ptr(), _DT[Vb.dtype], B, P, D, pooled.data_ptr(), _stream())
         ctx.save_for_backward(Vb, Lb, l_hat, g_hat, lnorm, gnorm)
         ctx.cfg = (float(sigma), V.dtype, L.dtype)
-        return l_hat, g_hat
+        return l_hat, g_hat, pooled
 
     @staticmethod
-    def backward(ctx, d_l_hat, d_g_hat):
+    def backward(ctx, d_l_hat, d_g_hat, d_pooled):
         Vb, Lb, l_hat, g_hat, lnorm, gnorm = ctx.saved_tensors
         sigma, v_dtype, l_dtype = ctx.cfg
         B, P, D = Vb.shape
@@ -382,15 +387,37 @@ class _SparcAlign(torch.autograd.Function):
         dL = _f32(B, T, D, device=dev)
         nbytes = _lib.lib().clipk_sparc_workspace_bytes(B, T, P, D, 1)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        g_add = None if d_pooled is None else (d_pooled.float() / P).contiguous()
         _lib.call("clipk_sparc_align_bwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, sigma, l_hat.data_ptr(),
-                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), d_g_hat.data_ptr(), d_l_hat.data_ptr(), 0,
-                  dV.data_ptr(), 1 if out_bf16 else 0, dL.data_ptr(), ws.data_ptr(), nbytes, _stream())
+                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), d_g_hat.data_ptr(), d_l_hat.data_ptr(),
+                  0 if g_add is None else g_add.data_ptr(), dV.data_ptr(), 1 if out_bf16 else 0, dL.data_ptr(),
+                  ws.data_ptr(), nbytes, _stream())
         return dV.to(v_dtype), dL.to(l_dtype), None
 
 
 def sparc_align(v_patch_embed, l_token_embed, sigma):
-    """Returns (l_token_embed_normalised, l_grouped_v_patch_embed_normalised), both fp32 [B,T,D]."""
-    return _SparcAlign.apply(v_patch_embed, l_token_embed, sigma)
+    """Returns (l_token_embed_normalised, l_grouped_v_patch_embed_normalised), both fp32 [B,T,D].
+
+    Also leaves the patch-mean of `v_patch_embed` on that tensor object (`_clipk_pooled`): `SparcLoss` picks it up
+    when it is handed the same tensor (the reference's `sparc.forward` returns `v_patch_embed` itself, pacl.py:478),
+    so the gradient of the global term's mean-pool is fused into the alignment backward."""
+    l_hat, g_hat, pooled = _SparcAlign.apply(v_patch_embed, l_token_embed, sigma)
+    try:
+        v_patch_embed._clipk_pooled = (pooled, v_patch_embed._version)
+    except Exception:      # exotic tensor subclasses without a __dict__: SparcLoss falls back to mean_dim1
+        pass
+    return l_hat, g_hat
+
+
+def pooled_patch_mean(v_patch_embed):
+    """mean over patches [B,D] fp32: the value `sparc_align` left on this tensor, else a fresh `mean_dim1`."""
+    tagged = getattr(v_patch_embed, "_clipk_pooled", None)
+    if tagged is not None:
+        del v_patch_embed._clipk_pooled                  # one use: its autograd graph is consumed by one backward
+        pooled, version = tagged
+        if version == v_patch_embed._version and pooled.device == v_patch_embed.device:
+            return pooled
+    return mean_dim1(v_patch_embed)
 
 
 class _MeanDim1(torch.autograd.Function):

@@ -121,7 +121,7 @@ class SparcLoss(ClipLoss):
         self.group = group
 
     def forward(self, v_patch_embed, l_token_embed, l_grouped_v_patch_embed, language_mask):
-        gi = Fk.normalize_rows(Fk.mean_dim1(v_patch_embed))
+        gi = Fk.normalize_rows(Fk.pooled_patch_mean(v_patch_embed))
         gt = Fk.normalize_rows(Fk.mean_dim1(l_token_embed))
         pg = self.group
         W = cdist.world_size(pg) if pg is not None else 1
