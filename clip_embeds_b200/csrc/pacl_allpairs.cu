@@ -249,7 +249,8 @@ static int launch_nd(bool pair, const OperandDesc* a, const OperandDesc* b, int 
 static int validate(int Bi, int Bt, int P, int D, int act, int group) {
   CLIPK_REQUIRE(Bi > 0 && Bt > 0 && P > 0 && D > 0, "pacl_allpairs: empty problem (Bi=%d Bt=%d P=%d D=%d)", Bi, Bt, P, D);
   CLIPK_REQUIRE(D % 8 == 0, "pacl_allpairs: D=%d must be a multiple of 8 (16-byte rows for TMA)", D);
-  CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES, "pacl_allpairs: bad activation %d", act);
+  CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES || act == CLIPK_ACT_SOFTMAX10,
+                "pacl_allpairs: bad activation %d", act);
   return 0;
 }
 

@@ -77,7 +77,7 @@ pacl_paired_fwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
     nsq = ptx::warp_sum(nsq);
     const float rn = 1.f / fmaxf(sqrtf(nsq), 1e-12f);
     const float s = r * rn;
-    const float sig = 1.f / (1.f + expf(-10.f * s));
+    const float sig = act == CLIPK_ACT_SOFTMAX10 ? expf(10.f * (s - 1.f)) : 1.f / (1.f + expf(-10.f * s));
     if (act_out != nullptr && lane == 0) act_out[(int64_t)b * P + p] = sig;
     const float a = (act == CLIPK_ACT_ONES) ? 1.f : sig;
 #pragma unroll
@@ -189,7 +189,10 @@ pacl_paired_bwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
     const float rn = 1.f / fmaxf(vn, 1e-12f);
     const float s = r * rn;
     float a = 1.f, ds = 0.f;
-    if (act != CLIPK_ACT_ONES) {
+    if (act == CLIPK_ACT_SOFTMAX10) {
+      a = expf(10.f * (s - 1.f));
+      ds = da * 10.f * a;
+    } else if (act != CLIPK_ACT_ONES) {
       a = 1.f / (1.f + expf(-10.f * s));
       ds = da * 10.f * a * (1.f - a);
     }
@@ -292,7 +295,7 @@ int clipk_pacl_paired_fwd(const void* V, const void* T, int dtype, int B, int v_
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(B >= 0 && P > 0 && D > 0 && v_div >= 1, "pacl_paired_fwd: bad shape B=%d P=%d D=%d v_div=%d", B, P, D, v_div);
   CLIPK_REQUIRE(D % 8 == 0, "pacl_paired_fwd: D=%d must be a multiple of 8", D);
-  CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES, "pacl_paired_fwd: bad activation %d", act);
+  CLIPK_REQUIRE(act >= CLIPK_ACT_SIGMOID10 && act <= CLIPK_ACT_SOFTMAX10, "pacl_paired_fwd: bad activation %d", act);
   if (B == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CLIPK_BF16)
@@ -309,7 +312,7 @@ int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P,
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(B >= 0 && P > 0 && D > 0, "pacl_paired_bwd: bad shape B=%d P=%d D=%d", B, P, D);
   CLIPK_REQUIRE(D % 8 == 0, "pacl_paired_bwd: D=%d must be a multiple of 8", D);
-  CLIPK_REQUIRE(act == CLIPK_ACT_SIGMOID10 || act == CLIPK_ACT_ONES, "pacl_paired_bwd: bad activation %d", act);
+  CLIPK_REQUIRE(act >= CLIPK_ACT_SIGMOID10 && act <= CLIPK_ACT_SOFTMAX10, "pacl_paired_bwd: bad activation %d", act);
   if (B == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CLIPK_BF16)

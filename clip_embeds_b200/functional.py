@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-ACT = {"sigmoid": 0, "sigmoid10": 0, "ones": 1}
+ACT = {"sigmoid": 0, "sigmoid10": 0, "ones": 1, "softmax": 2, "softmax10": 2}
 _DT = {torch.bfloat16: 0, torch.float32: 1}
 
 
@@ -86,10 +86,14 @@ class _PaclPaired(torch.autograd.Function):
         return dV, dT.to(ctx.t_dtype), None
 
 
-def patch_alignment(visual_patch_proj, text_cls_proj):
+def patch_alignment(visual_patch_proj, text_cls_proj, activation="sigmoid"):
     """sigmoid(10 * cos(patch, text)) -> [B, P] fp32 (pacl.py:120-133).  Not differentiable on its own; use
-    `pacl_pool` for the training path (activation + pooling + normalisation fused, one pass over V)."""
-    return _paired_forward(visual_patch_proj, text_cls_proj, ACT["sigmoid"], want_act=True)[3]
+    `pacl_pool` for the training path (activation + pooling + normalisation fused, one pass over V).
+    activation='softmax' returns softmax_p(10 * cos) (the kernel's un-normalised exp weights, normalised here)."""
+    a = _paired_forward(visual_patch_proj, text_cls_proj, ACT[activation], want_act=True)[3]
+    if ACT[activation] == ACT["softmax"]:
+        a = a / a.sum(dim=-1, keepdim=True)
+    return a
 
 
 def pacl_pool(visual_proj, text_proj, activation="sigmoid"):

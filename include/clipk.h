@@ -34,6 +34,11 @@ extern "C" {
 
 #define CLIPK_ACT_SIGMOID10 0 /* sigmoid(10*cos): reference parity, pacl.py:133 */
 #define CLIPK_ACT_ONES 1      /* activations overwritten with ones: the checked-in forward(), pacl.py:141-142 */
+/* softmax over the patches of 10 * cos (north_star (2); SURVEY Appendix A.1 lists it as the third activation, the
+ * reference itself has no such branch).  The pooled feature is L2-normalised afterwards, so the softmax denominator
+ * cancels: the kernels pool with a_p = exp(10 (s_p - 1)) (the -1 only keeps the weights in (0, 1]), whose Jacobian
+ * is the diagonal 10 a_p; act_out of the paired forward holds these UN-normalised weights. */
+#define CLIPK_ACT_SOFTMAX10 2
 
 const char* clipk_last_error(void);
 int clipk_version(void);

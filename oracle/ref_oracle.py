@@ -51,6 +51,11 @@ def pacl_forward(V, T, activation="sigmoid"):
     a = patch_alignment(V, T)
     if activation == "ones":
         a = torch.ones_like(a)
+    elif activation == "softmax":
+        # north_star (2) / SURVEY Appendix A.1 third activation (NO reference implementation: this branch restates
+        # the definition, it is not pinned by a reference output): softmax over the patches of 10 * cos
+        vn = l2n(V).transpose(-2, -1)
+        a = torch.softmax(10.0 * (l2n(T).unsqueeze(1) @ vn).squeeze(1), dim=-1)
     pooled = torch.sum(V * a.unsqueeze(-1), dim=1)
     return l2n(pooled), l2n(T)
 

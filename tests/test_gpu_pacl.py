@@ -124,6 +124,30 @@ def test_allpairs_dv_orientations(monkeypatch):
     assert e0[1] < 3e-2 and e1[1] < 3e-2 and e0[2] < 3e-2 and e1[2] < 3e-2
 
 
+def test_softmax_activation():
+    """Third activation of SURVEY Appendix A.1 / north_star (2): softmax over patches of 10 * cos.  The kernels pool
+    with the un-normalised exp weights (the L2-normalisation cancels the denominator); checked against the oracle's
+    restatement of the definition (no reference branch exists for it)."""
+    Fk, _ = _cuda()
+    V = O.rn(61, 6, 100, 128)
+    T = O.rn(62, 6, 128)
+    Vo, To = V.clone().requires_grad_(), T.clone().requires_grad_()
+    io, to = O.pacl_forward(Vo, To, "softmax")
+    (io * to).sum().backward()
+    Vg, Tg = V.cuda().requires_grad_(), T.cuda().requires_grad_()
+    ig, tg = Fk.pacl_pool(Vg, Tg, "softmax")
+    (ig * tg).sum().backward()
+    assert torch.allclose(ig.cpu(), io, atol=2e-6) and torch.allclose(tg.cpu(), to, atol=2e-6)
+    assert rel_l2(Vg.grad.cpu(), Vo.grad) < 1e-4 and rel_l2(Tg.grad.cpu(), To.grad) < 1e-4
+    a = Fk.patch_alignment(V.cuda(), T.cuda(), "softmax")
+    ao = torch.softmax(10.0 * torch.einsum("bd,bpd->bp", O.l2n(T), O.l2n(V)), dim=-1)
+    assert torch.allclose(a.cpu(), ao, atol=1e-6)
+    e = _allpairs_case(5, 40, 100, 128, seed=63, activation="softmax")
+    assert e[0] < 3e-2 and e[1] < 4e-2 and e[2] < 4e-2
+    e = _allpairs_case(5, 130, 576, 768, seed=64, activation="softmax", group=(-3, 2))
+    assert e[0] < 3e-2 and e[1] < 4e-2 and e[2] < 4e-2
+
+
 def test_allpairs_loss_golden(goldens):
     """Reference golden G6 (fp32 reference on fp32 inputs) vs the bf16 tensor-core path: bf16 input rounding is part of
     the error here, hence the looser loss tolerance."""
