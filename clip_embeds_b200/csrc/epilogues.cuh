@@ -309,7 +309,7 @@ struct Usq {
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (bwd)
 // acc = u_ik[d].  The gradient w.r.t. the un-normalised pooled vector is G_ik = alpha_ik t^_k - beta_ik u_ik; only its
 // u-part  Gn_ik = -beta_ik u_ik  is materialised (bf16, TMA store): the t^ part is folded analytically into the
-// consumers (DsDual adds alpha <t^,V>; the dV GEMM uses E^T T^ which already contains alpha a t^).
+// consumers (DsIn adds alpha <t^,V>; the dV GEMM uses E^T T^ which already contains alpha a t^).
 struct GNeg {
   static constexpr bool kTmaOut = true;
   struct Params {
@@ -324,71 +324,6 @@ struct GNeg {
   __device__ void chunk(int, int, int, float* v) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= nb;
-  }
-  __device__ void tile_end(int, int, int, int, int) {}
-};
-
-// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM1+GEMM3 (bwd)
-// Dual accumulators over the same V tile:  x = <T_k, V_ip> (raw score, recomputed)  and  d = <Gn_ik, V_ip>.
-//   s  = x rnT rnV,  a = sigmoid(10 s)                              (recomputed in registers: never re-read from HBM)
-//   da = alpha_ik rnT_k x + d   ( = <G_ik, V_ip> ),   ds = da * 10 a (1 - a)
-//   E[i,k,p] = ds * rnV[i,p] + alpha_ik a     (TMA store; operand of dt^ += E V  and of dV += E^T T^)
-//   dsdot[i,p] += sum_k ds * s                (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
-struct DsDual {
-  static constexpr bool kTmaOut = true;
-  static constexpr bool kDual = true;
-  using Side = float;          // lane l holds rnV[i, n + l]
-  struct Params {
-    eng::OutDesc out;        // E [batch][M][Ppad]
-    const float* rnV;        // [batch][P]
-    const float* rnT;        // [M]
-    const float* alpha;      // [batch][M]
-    float* dsdot;            // [batch][P]
-    int M, P, Ppad, act;
-  };
-  Params p;
-  float rt, al;
-  __device__ explicit DsDual(const Params& pp) : p(pp), rt(0.f), al(0.f) {}
-  __device__ void tile_begin(int b, int m, int) {
-    rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
-    al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f;
-  }
-  __device__ Side pre(int b, int, int n) const {
-    const int lane = (int)ptx::lane_id();
-    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
-  }
-  __device__ void chunk2(int b, int m, int n, float* x, float* d, const Side& rn_l) {
-    const int lane = (int)ptx::lane_id();
-    const bool ones = p.act == CLIPK_ACT_ONES;
-    const float gate = (m < p.M && !ones) ? 10.f : 0.f;
-    const float art = al * rt;
-    const float rt5 = 5.f * rt;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const float r0 = __shfl_sync(0xffffffffu, rn_l, j);        // 0 for p >= P: masks the pad columns
-      const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
-      const float xs0 = x[j] * r0, xs1 = x[j + 1] * r1;
-      float t0, t1;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(xs0 * rt5));
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(xs1 * rt5));
-      float a0 = ones ? 1.f : fmaf(0.5f, t0, 0.5f);
-      float a1 = ones ? 1.f : fmaf(0.5f, t1, 0.5f);
-      bf16_round_pair(a0, a1);
-      const float ds0 = fmaf(art, x[j], d[j]) * gate * a0 * (1.f - a0);
-      const float ds1 = fmaf(art, x[j + 1], d[j + 1]) * gate * a1 * (1.f - a1);
-      x[j] = fmaf(al, a0, ds0 * r0);                              // E
-      x[j + 1] = fmaf(al, a1, ds1 * r1);
-      d[j] = ds0 * xs0 * rt;                                      // ds * s  (0 in pad columns / invalid rows)
-      d[j + 1] = ds1 * xs1 * rt;
-    }
-    if (n + 32 > p.P) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n + j >= p.P) x[j] = 0.f;
-    }
-    const float cs = ptx::warp_colsum32(d);   // lane j: sum over this warp's 32 rows of column n + j
-    const int col = n + lane;
-    if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };
