@@ -70,3 +70,40 @@ def test_pacl_cliploss_bf16():
     assert abs(loss.item() - lo.item()) < 2e-3 * abs(lo.item())
     assert rel_l2(img.grad.float().cpu(), io.grad) < 2e-2
     assert rel_l2(txt.grad.float().cpu(), to.grad) < 2e-2
+
+
+def test_negclip_full_size_rank_share():
+    """BASELINE.json configs[3] at full size, one rank's share at W = 8: b = 4096 local images against N + sum H =
+    32768 + 8192 gathered texts, and the b + H_r local texts against the 32768 gathered images (loss.py:156-164 with
+    `usehardtext`).  Too large for the CPU oracle in seconds: the tensor-core path (logits never written) is compared
+    with the same formula evaluated by fp32 torch ops on the same bf16-rounded features (logits materialised),
+    plus two size-independent properties: rows with ignore_index contribute no gradient, and the image-side loss is
+    invariant to a permutation of the gathered texts that keeps the positives in place."""
+    import torch.nn.functional as F
+    import clip_embeds_b200.functional as Fk
+    b, N, H, D, Hr = 4096, 32768, 8192, 768, 1024
+    g = torch.Generator().manual_seed(5)
+    f = lambda n: torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=-1).to(torch.bfloat16).cuda()
+    img_loc, txt_all, txt_loc, img_all = f(b), f(N + H), f(b + Hr), f(N)
+    lab_t = torch.full((b + Hr,), -100, dtype=torch.int64, device="cuda")
+    lab_t[:b] = torch.arange(b, device="cuda") + 3 * b          # rank 3's label offset
+    ours = [t.detach().requires_grad_() for t in (img_loc, txt_all, txt_loc, img_all)]
+    li = Fk.feat_row_ce(ours[0], ours[1], 100.0, 0.0, None, 3 * b)
+    lt = Fk.feat_row_ce(ours[2], ours[3], 100.0, 0.0, lab_t, 0)
+    ((li + lt) / 2).backward()
+    ref = [t.detach().float().requires_grad_() for t in (img_loc, txt_all, txt_loc, img_all)]
+    Li = 100.0 * ref[0] @ ref[1].T
+    Lt = 100.0 * ref[2] @ ref[3].T
+    lri = F.cross_entropy(Li, torch.arange(b, device="cuda") + 3 * b)
+    lrt = F.cross_entropy(Lt, lab_t, ignore_index=-100)
+    ((lri + lrt) / 2).backward()
+    assert abs(li.item() - lri.item()) < 2e-3 * max(1.0, lri.item())
+    assert abs(lt.item() - lrt.item()) < 2e-3 * max(1.0, lrt.item())
+    for o, r in zip(ours, ref):
+        assert rel_l2(o.grad.float(), r.grad) < 2e-2
+    assert ours[2].grad[b:].abs().max().item() == 0.0            # hard-negative text rows are ignore_index rows
+    # permuting the negatives among themselves does not change the image-side loss
+    perm = torch.arange(N + H, device="cuda")
+    perm[4 * b:] = perm[4 * b:].flip(0)
+    li_p = Fk.feat_row_ce(img_loc, txt_all[perm].contiguous(), 100.0, 0.0, None, 3 * b)
+    assert abs(li_p.item() - li.item()) < 1e-4 * max(1.0, li.item())
