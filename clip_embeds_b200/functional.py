@@ -9,6 +9,8 @@ Reference call sites (relative to the reference root, PACL = Patch-Aligned-Contr
   eval scoring                  PACL/eval_pacl.py:50-57, :303-309; PACL/eval_llm2pacl.py:62-67
   open_clip ClipLoss            open_clip/src/open_clip/loss.py:89-193
 """
+import os
+
 import torch
 
 from . import _lib
@@ -118,6 +120,10 @@ def default_schedule(Bt, P, D, backward=True):
     sized image group (DESIGN.md "mega kernel"); group < 0 = the same with -group images per group and `lanes` groups
     in lock-step; group > 0 = the staged path (one engine launch per GEMM, `group` images per launch on `lanes`
     internal streams)."""
+    env = os.environ.get("CLIPK_AP_SCHEDULE")            # e.g. "128:2" (staged) or "-16:3" (persistent kernel)
+    if env:
+        parts = [int(x) for x in env.split(":")]
+        return (parts[0], parts[1] if len(parts) > 1 else 1)
     return _SCHEDULE["bwd" if backward else "fwd"]
 
 
