@@ -36,6 +36,9 @@ SIGNATURES = {
     "clipk_ce_rows_grad": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "clipk_sgemm_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_f32,
                                 c_vp]),
+    "clipk_gemm_f32_split_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "clipk_gemm_f32_split": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_f32,
+                                     c_int, c_vp, c_sz, c_vp]),
     "clipk_ce_feat_workspace_bytes": (c_sz, [c_int, c_int]),
     "clipk_ce_feat_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz,
                                   c_vp]),

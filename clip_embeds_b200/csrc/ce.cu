@@ -400,6 +400,23 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, const float* _
 static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 constexpr int kCeChunkRows = 4096;
 
+// The feature-CE GEMMs run on the CTA-pair engine (256-row tiles) whenever the problem has more than one 128-row
+// tile; CLIPK_CE_ENGINE=1|2 forces one (A/B measurements, pipeline tests).
+static int ce_engine(int M) {
+  static const int forced = [] {
+    const char* e = getenv("CLIPK_CE_ENGINE");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return forced;
+  return M > eng::BM ? 2 : 1;
+}
+template <int BN, bool A_MN, bool B_MN, class Epi>
+static int ce_launch(int engine, const OperandDesc* a, const OperandDesc* b, const int* ks, int M, int N,
+                     const typename Epi::Params& ep, cudaStream_t st) {
+  if (engine == 2) return launch_gemm2<BN, A_MN, B_MN, Epi>(a, b, 1, ks, ks, M, N, 1, ep, st);
+  return launch_gemm<BN, A_MN, B_MN, Epi>(a, b, 1, ks, ks, M, N, 1, ep, st);
+}
+
 struct CeWorkspace {
   float2* part;
   float* pos;
@@ -434,7 +451,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   const int tiles_n = 2 * ((N + 255) / 256);   // one partial per (n-tile, epilogue-warp half)
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
   epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
-  CLIPK_TRY(launch_gemm<256, false, false, epi::LsePart>(&a, &b, 1, ks, ks, M, N, 1, ep, st));
+  CLIPK_TRY((ce_launch<256, false, false, epi::LsePart>(ce_engine(M), &a, &b, ks, M, N, ep, st)));
   lse_merge_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
   clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
@@ -459,7 +476,7 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
       epi::DlOut::Params ep{row_lse + m0, row_w + m0, labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0),
                             w.dL, ldd, mc, N, scale, bias};
-      CLIPK_TRY(launch_gemm<256, false, false, epi::DlOut>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st));
+      CLIPK_TRY((ce_launch<256, false, false, epi::DlOut>(ce_engine(mc), &a, &b, ksD, mc, N, ep, st)));
     }
     // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
     if (dX != nullptr) {
@@ -468,7 +485,7 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
       const int ks[1] = {(N + 63) / 64};
       epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX};
-      CLIPK_TRY(launch_gemm<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, 1, ep, st));
+      CLIPK_TRY((ce_launch<256, false, true, epi::Store<false>>(ce_engine(mc), &a, &b, ks, mc, D, ep, st)));
     }
     // dY (+)= scale * dL^T X[m0:m0+mc]        (A = dL MN-major (rows = n), B = X MN-major)
     if (dY != nullptr) {
@@ -477,7 +494,7 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = X + (int64_t)m0 * D; b.mn_major = true; b.rows = D; b.k = mc; b.ld = D;
       const int ks[1] = {(mc + 63) / 64};
       epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0};
-      CLIPK_TRY(launch_gemm<256, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, N, D, 1, ep, st));
+      CLIPK_TRY((ce_launch<256, true, true, epi::Store<false>>(ce_engine(N), &a, &b, ks, N, D, ep, st)));
     }
   }
   return 0;

@@ -271,6 +271,64 @@ def score_infonce(scores, offset=0, group=None):
     return _ScoreInfoNCE.apply(scores, int(offset), group)
 
 
+# --------------------------------------------------------------------------------------------- fp32 GEMM
+_SPLIT_MIN_WORK = 1 << 21          # M*N*K below this: the fp32 SIMT kernel (launch-bound either way)
+
+
+def _gemm_f32(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, alpha, accumulate=False):
+    """C[m,n] (+)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] on fp32 tensors.  Large problems run on the
+    tensor cores with fp32 accuracy (bf16 x 3 split, six products folded into one tcgen05 GEMM); small ones on the
+    fp32 SIMT kernel.  Both are kernels of libclipk (no library / eager path)."""
+    st = _stream()
+    if M * N * K >= _SPLIT_MIN_WORK:
+        nbytes = _lib.lib().clipk_gemm_f32_split_workspace_bytes(M, N, K)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=C.device)
+        _lib.call("clipk_gemm_f32_split", A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, C.data_ptr(), ldc, M, N, K,
+                  float(alpha), 1 if accumulate else 0, ws.data_ptr(), nbytes, st)
+    else:
+        _lib.call("clipk_sgemm_f32", A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, C.data_ptr(), ldc, M, N, K,
+                  float(alpha), 1.0 if accumulate else 0.0, st)
+
+
+class _MatmulNT(torch.autograd.Function):
+    """L = alpha * X @ Y.T for fp32 features (pacl.py:499: `logit_scale * image_features @ text_features.T`)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, alpha):
+        _need_cuda(X, Y)
+        Xc, Yc = X.float().contiguous(), Y.float().contiguous()
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        L = _f32(M, N, device=Xc.device)
+        _gemm_f32(Xc, D, 1, Yc, 1, D, L, N, M, N, D, alpha)
+        ctx.save_for_backward(Xc, Yc)
+        ctx.cfg = (float(alpha), X.dtype, Y.dtype)
+        return L
+
+    @staticmethod
+    def backward(ctx, dL):
+        Xc, Yc = ctx.saved_tensors
+        alpha, xdt, ydt = ctx.cfg
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        dL = dL.float().contiguous()
+        dX, dY = _f32(M, D, device=Xc.device), _f32(N, D, device=Xc.device)
+        _gemm_f32(dL, N, 1, Yc, D, 1, dX, D, M, D, N, alpha)          # dX = alpha * dL Y
+        _gemm_f32(dL, 1, N, Xc, D, 1, dY, D, N, D, M, alpha)          # dY = alpha * dL^T X
+        return dX.to(xdt), dY.to(ydt), None
+
+
+def symmetric_infonce(X, Y, scale):
+    """1/2 [CE(scale X Y^T, I) + CE(scale Y X^T, I)] (pacl.py:498-514).  fp32 features: ONE logits GEMM (the text-side
+    logits are its transpose), row + column CE on the fp32 matrix, two gradient GEMMs; bf16 features: the
+    tensor-core feature CE (logits never written)."""
+    if X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16:
+        return (feat_row_ce(X, Y, scale) + feat_row_ce(Y, X, scale)) / 2
+    if X.shape[0] != Y.shape[0]:
+        raise ValueError(f"symmetric InfoNCE needs as many rows in X as in Y ({X.shape[0]} vs {Y.shape[0]})")
+    return score_infonce(_MatmulNT.apply(X, Y, float(scale)), 0, None)
+
+
 # --------------------------------------------------------------------------------------------- CE from features
 class _FeatRowCE(torch.autograd.Function):
     """sum over valid rows of CE(scale * X Y^T + bias, labels) and the number of valid rows.
@@ -308,8 +366,7 @@ class _FeatRowCE(torch.autograd.Function):
             logits = _f32(M, N, device=dev)
             if bi != 0.0:
                 logits.fill_(bi)
-            _lib.call("clipk_sgemm_f32", Xc.data_ptr(), D, 1, Yc.data_ptr(), 1, D, logits.data_ptr(), N, M, N, D, sc,
-                      1.0 if bi != 0.0 else 0.0, st)
+            _gemm_f32(Xc, D, 1, Yc, 1, D, logits, N, M, N, D, sc, accumulate=bi != 0.0)
             _lib.call("clipk_ce_rows", logits.data_ptr(), M, N, N, lab_ptr, label_offset, row_lse.data_ptr(),
                       row_loss.data_ptr(), st)
             ctx.ws = None
@@ -341,8 +398,8 @@ class _FeatRowCE(torch.autograd.Function):
             _lib.call("clipk_ce_rows_grad", logits.data_ptr(), M, N, N, row_lse.data_ptr(), lab_ptr, label_offset,
                       row_w.data_ptr(), dL.data_ptr(), st)
             # dX = scale * dL Y ; dY = scale * dL^T X
-            _lib.call("clipk_sgemm_f32", dL.data_ptr(), N, 1, Yc.data_ptr(), D, 1, dX.data_ptr(), D, M, D, N, sc, 0.0, st)
-            _lib.call("clipk_sgemm_f32", dL.data_ptr(), 1, N, Xc.data_ptr(), D, 1, dY.data_ptr(), D, N, D, M, sc, 0.0, st)
+            _gemm_f32(dL, N, 1, Yc, D, 1, dX, D, M, D, N, sc)
+            _gemm_f32(dL, 1, N, Xc, D, 1, dY, D, N, D, M, sc)
         dscale = None
         if ctx.scale_needs_grad:      # d/dscale sum(dlogits * x.y) = <dX, X> / scale
             dscale = (dX * Xc.float()).sum() / sc

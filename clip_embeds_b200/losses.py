@@ -22,9 +22,7 @@ class ClipLoss(nn.Module):
         self.logit_scale = 1.0 / temperature
 
     def forward(self, image_features, text_features):
-        li = Fk.feat_row_ce(image_features, text_features, self.logit_scale)
-        lt = Fk.feat_row_ce(text_features, image_features, self.logit_scale)
-        return (li + lt) / 2
+        return Fk.symmetric_infonce(image_features, text_features, self.logit_scale)
 
 
 class PaclAllPairsLoss(nn.Module):
@@ -139,8 +137,6 @@ class SparcLoss(ClipLoss):
             local_part = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale, msum)
             total = self.global_weight * global_part + self.local_weight * local_part
             return cdist.all_reduce_sum_with_grad(total, pg)
-        li = Fk.feat_row_ce(gi, gt, self.logit_scale)
-        lt = Fk.feat_row_ce(gt, gi, self.logit_scale)
-        global_loss = (li + lt) / 2
+        global_loss = Fk.symmetric_infonce(gi, gt, self.logit_scale)
         local_loss = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale)
         return self.global_weight * global_loss + self.local_weight * local_loss

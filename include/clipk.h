@@ -124,6 +124,15 @@ int clipk_ce_rows_grad(const float* L, int M, int N, int64_t ld, const float* ro
 int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
                     int64_t ldc, int M, int N, int K, float alpha, float beta, void* stream);
 
+/* The same product with fp32 accuracy on the bf16 tensor cores: every operand value is split into three bf16 terms
+ * (h + m + l = 24 mantissa bits) and the six significant cross products are folded into one tcgen05 GEMM over
+ * K' = 6 * roundup(K, 64) (fp32 accumulation in TMEM).  Same stride convention as clipk_sgemm_f32; `accumulate`
+ * != 0 adds to C (beta = 1).  `workspace` (128-byte aligned) holds the split operands. */
+size_t clipk_gemm_f32_split_workspace_bytes(int M, int N, int K);
+int clipk_gemm_f32_split(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                         int64_t ldc, int M, int N, int K, float alpha, int accumulate, void* workspace,
+                         size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * bf16 feature cross-entropy on the tcgen05 engine (NegCLIP ClipLoss, loss.py:137-193; PACL ClipLoss, pacl.py:489-514):
  *   logits = scale * X Y^T + bias, X bf16 [M,D], Y bf16 [N,D]; the [M,N] logits are never written.

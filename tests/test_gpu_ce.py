@@ -107,3 +107,55 @@ def test_negclip_full_size_rank_share():
     perm[4 * b:] = perm[4 * b:].flip(0)
     li_p = Fk.feat_row_ce(img_loc, txt_all[perm].contiguous(), 100.0, 0.0, None, 3 * b)
     assert abs(li_p.item() - li.item()) < 1e-4 * max(1.0, li.item())
+
+
+@pytest.mark.parametrize("shape", [(512, 512, 768), (1024, 768, 1024), (300, 200, 100), (129, 257, 65)])
+def test_gemm_f32_split_matches_fp64(shape):
+    """fp32 GEMM on the bf16 tensor cores (3-term split, six products in one tcgen05 GEMM) against an fp64 product,
+    in the three operand layouts the fp32 feature path uses (X Y^T, dL Y, dL^T X).  Tolerance: max abs error
+    <= 2e-6 * sqrt(K) * max|a| max|b| -- the error level of an fp32-accumulating GEMM."""
+    import clip_embeds_b200.functional as Fk
+    M, N, K = shape
+    g = torch.Generator().manual_seed(11)
+    for layout in ("nt", "nn", "tn"):
+        A = torch.randn(M, K, generator=g).cuda()
+        B = torch.randn(N, K, generator=g).cuda()
+        ref = (A.double() @ B.double().T) * 0.5
+        C = torch.full((M, N), float("nan"), device="cuda")
+        if layout == "nt":        # A [M,K] K-major, B [N,K] K-major
+            Fk._gemm_f32(A, K, 1, B, 1, K, C, N, M, N, K, 0.5)
+        elif layout == "nn":      # B stored [K,N]
+            Bt = B.T.contiguous()
+            Fk._gemm_f32(A, K, 1, Bt, N, 1, C, N, M, N, K, 0.5)
+        else:                     # A stored [K,M], B stored [K,N]
+            At, Bt = A.T.contiguous(), B.T.contiguous()
+            Fk._gemm_f32(At, 1, M, Bt, N, 1, C, N, M, N, K, 0.5)
+        err = (C.double() - ref).abs().max().item()
+        tol = 2e-6 * (K ** 0.5) * A.abs().max().item() * B.abs().max().item()
+        print(f"gemm_f32_split {shape} {layout}: max abs err {err:.3e} (tol {tol:.3e})")
+        assert err <= tol
+        C2 = torch.ones(M, N, device="cuda")
+        if layout == "nt":
+            Fk._gemm_f32(A, K, 1, B, 1, K, C2, N, M, N, K, 0.5, accumulate=True)
+            assert (C2.double() - 1.0 - ref).abs().max().item() <= tol + 1e-6
+
+
+@pytest.mark.parametrize("B", [64, 512, 1024])
+def test_pacl_cliploss_fp32(B):
+    """fp32 ClipLoss (reference training dtype): one logits GEMM on the tensor cores at fp32 accuracy + row/column CE,
+    against the oracle.  Tolerance: loss 1e-5 relative, gradients 2e-5 relative L2."""
+    from clip_embeds_b200.losses import ClipLoss
+    D = 768
+    io = O.l2n(O.rn(61, B, D)).requires_grad_()
+    to = O.l2n(O.rn(62, B, D)).requires_grad_()
+    lo = O.pacl_clip_loss(io, to, 0.1)
+    lo.backward()
+    img = io.detach().cuda().requires_grad_()
+    txt = to.detach().cuda().requires_grad_()
+    loss = ClipLoss(0.1)(img, txt)
+    loss.backward()
+    print(f"cliploss fp32 B={B}: {loss.item():.7f} vs {lo.item():.7f}; rel dimg {rel_l2(img.grad.cpu(), io.grad):.2e} "
+          f"dtxt {rel_l2(txt.grad.cpu(), to.grad):.2e}")
+    assert abs(loss.item() - lo.item()) < 1e-5 * abs(lo.item())
+    assert rel_l2(img.grad.cpu(), io.grad) < 2e-5
+    assert rel_l2(txt.grad.cpu(), to.grad) < 2e-5
