@@ -375,6 +375,49 @@ struct DlOut {
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
+// The same through the engine's TMA-store path (CTA-pair engine: every epilogue warp stages its [32 x 32] bf16 chunk and
+// writes it with its own TMA store; rows >= M and columns >= N are clipped by the output map's extents).
+struct DlOutTma {
+  static constexpr bool kTmaOut = true;
+  struct Params {
+    eng::OutDesc out;        // dL [M][ldd] bf16, extents (M, N)
+    const float* lse;        // [M]
+    const float* w;          // [M]
+    const int64_t* labels;   // nullable
+    int64_t label_offset;
+    int M, N;
+    float scale, bias;
+  };
+  Params p;
+  float nlse, w;
+  int lab;                   // label column of this row, or -1
+  __device__ explicit DlOutTma(const Params& pp) : p(pp), nlse(0.f), w(0.f), lab(-1) {}
+  __device__ void tile_begin(int, int m, int) {
+    w = 0.f;
+    nlse = 0.f;
+    lab = -1;
+    if (m < p.M) {
+      nlse = fmaf(p.bias, 1.f, -p.lse[m]);          // bias - lse: logit - lse = acc * scale + (bias - lse)
+      w = p.w[m];
+      const int64_t l = p.labels != nullptr ? p.labels[m] : (int64_t)m + p.label_offset;
+      lab = (l >= 0 && l < p.N) ? (int)l : -1;
+    }
+  }
+  __device__ void chunk(int, int, int n, float* v) {
+    // w (exp(logit - lse) - [n + j == label]);  rows with w == 0 (ignored rows, rows past M) give exact zeros
+    const float k2 = p.scale * 1.4426950408889634f, c2 = nlse * 1.4426950408889634f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (w == 0.f) ? 0.f : w * exp2f(fmaf(v[j], k2, c2));
+    const int rel = lab - n;
+    if (rel >= 0 && rel < 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j == rel) v[j] -= w;
+    }
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
 }  // namespace epi
 
 namespace clipk {
@@ -409,6 +452,13 @@ static int ce_engine(int M) {
   }();
   if (forced == 1 || forced == 2) return forced;
   return M > eng::BM ? 2 : 1;
+}
+static bool ce_dl_tma() {       // CLIPK_CE_DLTMA=0: per-thread stores of dL (A/B measurements)
+  static const bool on = [] {
+    const char* e = getenv("CLIPK_CE_DLTMA");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 template <int BN, bool A_MN, bool B_MN, class Epi>
 static int ce_launch(int engine, const OperandDesc* a, const OperandDesc* b, const int* ks, int M, int N,
@@ -474,9 +524,15 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       OperandDesc a, b;
       a.ptr = X + (int64_t)m0 * D; a.rows = mc; a.k = D; a.ld = D;
       b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
-      epi::DlOut::Params ep{row_lse + m0, row_w + m0, labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0),
-                            w.dL, ldd, mc, N, scale, bias};
-      CLIPK_TRY((ce_launch<256, false, false, epi::DlOut>(ce_engine(mc), &a, &b, ksD, mc, N, ep, st)));
+      if (ce_engine(mc) == 2 && ce_dl_tma()) {
+        epi::DlOutTma::Params ep{{w.dL, ldd, (int64_t)mc * ldd, mc, N, 1}, row_lse + m0, row_w + m0,
+                                 labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0), mc, N, scale, bias};
+        CLIPK_TRY((launch_gemm2<256, false, false, epi::DlOutTma>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st)));
+      } else {
+        epi::DlOut::Params ep{row_lse + m0, row_w + m0, labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0),
+                              w.dL, ldd, mc, N, scale, bias};
+        CLIPK_TRY((ce_launch<256, false, false, epi::DlOut>(ce_engine(mc), &a, &b, ksD, mc, N, ep, st)));
+      }
     }
     // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
     if (dX != nullptr) {

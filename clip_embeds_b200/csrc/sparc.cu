@@ -36,6 +36,29 @@ struct SparcDv {
   }
   __device__ void tile_end(int, int, int, int, int) {}
 };
+// The same as a TMA-store functor (bf16 dV with 16-byte aligned rows, CTA-pair engine): lane l holds gadd[b][n + l] of
+// the chunk (loaded one chunk ahead), broadcast by shuffle.
+struct SparcDvTma {
+  static constexpr bool kTmaOut = true;
+  using Side = float;
+  struct Params {
+    eng::OutDesc out;    // dV [batch][M][N] bf16
+    const float* gadd;   // [batch][N] or nullptr
+    int N;
+  };
+  Params p;
+  __device__ explicit SparcDvTma(const Params& pp) : p(pp) {}
+  __device__ void tile_begin(int, int, int) {}
+  __device__ Side pre(int b, int, int n) const {
+    const int lane = (int)ptx::lane_id();
+    return (p.gadd != nullptr && n + lane < p.N) ? __ldg(p.gadd + (int64_t)b * p.N + n + lane) : 0.f;
+  }
+  __device__ void chunk(int, int, int, float* v, const Side& g_l) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, g_l, j);
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
 }  // namespace epi
 
 namespace clipk {
@@ -398,8 +421,15 @@ int sparc_align_bwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T
     a[1] = a[0]; a[1].ptr = w.dS;
     b[1] = b[0]; b[1].ptr = L;
     const int ks[2] = {(T + 63) / 64, (T + 63) / 64};
-    epi::SparcDv::Params ep{g_add, dV, P, D, dv_bf16};
-    CLIPK_TRY(launch_bn<epi::SparcDv, true, true>(D, a, b, 2, ks, P, D, B, ep, st));
+    if (dv_bf16 && D % 8 == 0 && (reinterpret_cast<uintptr_t>(dV) & 15) == 0 && P > eng::BM) {
+      // bf16 dV: CTA-pair engine, every epilogue warp writes its [32 x 32] chunk with its own TMA store
+      epi::SparcDvTma::Params ep{{dV, D, (int64_t)P * D, P, D, B}, g_add, D};
+      if (D > 128) CLIPK_TRY((launch_gemm2<256, true, true, epi::SparcDvTma>(a, b, 2, ks, ks, P, D, B, ep, st)));
+      else CLIPK_TRY((launch_gemm2<128, true, true, epi::SparcDvTma>(a, b, 2, ks, ks, P, D, B, ep, st)));
+    } else {
+      epi::SparcDv::Params ep{g_add, dV, P, D, dv_bf16};
+      CLIPK_TRY(launch_bn<epi::SparcDv, true, true>(D, a, b, 2, ks, P, D, B, ep, st));
+    }
   }
   return 0;
 }
@@ -488,6 +518,24 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bf
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __float2bfloat16(x[i]);
 }
+// 8 values per thread: two 16-byte loads, one 16-byte store (n8 = n / 8; both pointers 16-byte aligned)
+__global__ void cast_bf16x8_kernel(const float4* __restrict__ x, int64_t n8, uint4* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+  y[i] = make_uint4(ptx::pack_bf16x2(a.x, a.y), ptx::pack_bf16x2(a.z, a.w), ptx::pack_bf16x2(b.x, b.y),
+                    ptx::pack_bf16x2(b.z, b.w));
+}
+static void launch_cast_bf16(const float* x, int64_t n, __nv_bfloat16* y, cudaStream_t st) {
+  if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const int64_t n8 = n / 8;
+    cast_bf16x8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), n8,
+                                                                     reinterpret_cast<uint4*>(y));
+  } else {
+    cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, y);
+  }
+  clipk::count_launches(1);
+}
 
 struct LocalWs {
   __nv_bfloat16 *a16, *b16, *dZ;
@@ -510,10 +558,8 @@ static int sparc_local_logits(const float* a, const float* b, int B, int T, int 
                               cudaStream_t st) {
   const int Tp = rup(T, 8);
   const int64_t n = (int64_t)B * T * D;
-  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, w.a16);
-  clipk::count_launches(1);
-  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b, n, w.b16);
-  clipk::count_launches(1);
+  launch_cast_bf16(a, n, w.a16, st);
+  launch_cast_bf16(b, n, w.b16, st);
   OperandDesc oa, ob;
   oa.ptr = w.a16; oa.rows = T; oa.k = D; oa.ld = D; oa.batch = B; oa.batch_stride = (int64_t)T * D; oa.bmul = 1;
   ob.ptr = w.b16; ob.rows = T; ob.k = D; ob.ld = D; ob.batch = B; ob.batch_stride = (int64_t)T * D; ob.bmul = 1;

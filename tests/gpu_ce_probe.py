@@ -52,6 +52,12 @@ def neg_fwd():
 
 
 flop = 6.0 * (b * (N + H) + (b + H // 8) * N) * D
+if len(sys.argv) > 1 and sys.argv[1] == "once":          # for ncu: one warm step, one profiled step
+    neg()
+    torch.cuda.synchronize()
+    neg()
+    torch.cuda.synchronize()
+    sys.exit(0)
 t = timed(neg)
 tf = timed(neg_fwd)
 print(f"engine={os.environ.get('CLIPK_CE_ENGINE', 'auto')} negclip share fwd+bwd {t:.3f} ms ({flop / t / 1e9:.0f} TF/s algorithmic), "
