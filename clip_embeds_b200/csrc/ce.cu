@@ -38,33 +38,32 @@ __global__ void ce_rows_kernel(const float* __restrict__ L, int M, int N, int64_
   }
 }
 
-// column-wise (max, sumexp) over the M local rows.  block = 32 columns x 8 row-lanes.
-__global__ void ce_cols_kernel(const float* __restrict__ L, int M, int N, int64_t ld, float* __restrict__ col_max,
-                               float* __restrict__ col_sum) {
-  __shared__ float smx[8][33], ssm[8][33];
+// column-wise (max, sumexp) over the M local rows.  block = 32 columns x 32 row-lanes; two passes (max, then
+// sum exp(v - max)) so that every load / exp of a thread is independent of the previous one (the one-pass online form is
+// a serial dependency chain of M / lanes exps per thread).
+__global__ void __launch_bounds__(1024) ce_cols_kernel(const float* __restrict__ L, int M, int N, int64_t ld,
+                                                        float* __restrict__ col_max, float* __restrict__ col_sum) {
+  __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
-  float mx = -INFINITY, sm = 0.f;
-  if (n < N) {
-    for (int m = ty; m < M; m += 8) {
-      const float v = L[(int64_t)m * ld + n];
-      if (v > mx) {
-        sm = sm * expf(mx - v) + 1.f;
-        mx = v;
-      } else {
-        sm += expf(v - mx);
-      }
-    }
-  }
-  smx[ty][tx] = mx;
-  ssm[ty][tx] = sm;
+  float mx = -INFINITY;
+  if (n < N)
+    for (int m = ty; m < M; m += 32) mx = fmaxf(mx, L[(int64_t)m * ld + n]);
+  red[ty][tx] = mx;
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) gm = fmaxf(gm, red[j][tx]);
+  __syncthreads();
+  float sm = 0.f;
+  if (n < N && gm > -INFINITY)
+    for (int m = ty; m < M; m += 32) sm += expf(L[(int64_t)m * ld + n] - gm);
+  red[ty][tx] = sm;
   __syncthreads();
   if (ty == 0 && n < N) {
-    float gm = -INFINITY;
-    for (int j = 0; j < 8; ++j) gm = fmaxf(gm, smx[j][tx]);
     float gs = 0.f;
-    for (int j = 0; j < 8; ++j)
-      if (smx[j][tx] > -INFINITY) gs += ssm[j][tx] * expf(smx[j][tx] - gm);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) gs += red[j][tx];
     col_max[n] = gm;
     col_sum[n] = gs;
   }
@@ -575,7 +574,7 @@ int clipk_ce_rows(const float* L, int M, int N, int64_t ld, const int64_t* label
 int clipk_ce_cols(const float* L, int M, int N, int64_t ld, float* col_max, float* col_sum, void* stream) {
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(M >= 0 && N > 0 && ld >= N, "ce_cols: bad shape M=%d N=%d ld=%lld", M, N, (long long)ld);
-  clipk::ce_cols_kernel<<<(N + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, col_max, col_sum);
+  clipk::ce_cols_kernel<<<(N + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(L, M, N, ld, col_max, col_sum);
   clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -94,20 +94,20 @@ struct DthSlabs {
 };
 __global__ void dtext_finalize_kernel(const __nv_bfloat16* __restrict__ T, const float* __restrict__ rnT,
                                       DthSlabs slabs, int lanes, int nslab, int Bt, int D, float* __restrict__ dT) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= Bt) return;
-  const int lane = threadIdx.x & 31;
+  // one block per text row: the slab sums of a row are (lanes * nslab) independent coalesced loads per thread
+  __shared__ float red[32];
+  const int row = blockIdx.x;
   const float rt = rnT[row];
   float dot = 0.f;
-  for (int d = lane; d < D; d += 32) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float g = 0.f;
     for (int l = 0; l < lanes; ++l)
       for (int s2 = 0; s2 < nslab; ++s2) g += slabs.p[l][((int64_t)s2 * Bt + row) * D + d];
     slabs.p[0][(int64_t)row * D + d] = g;   // lane 0 / slab 0 now holds the total (each thread touches only its own d)
     dot = fmaf(__bfloat162float(T[(int64_t)row * D + d]) * rt, g, dot);
   }
-  dot = ptx::warp_sum(dot);
-  for (int d = lane; d < D; d += 32) {
+  dot = simt::block_sum(dot, red);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float th = __bfloat162float(T[(int64_t)row * D + d]) * rt;
     dT[(int64_t)row * D + d] = rt * (slabs.p[0][(int64_t)row * D + d] - th * dot);
   }
@@ -637,7 +637,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
   DthSlabs slabs{};
   for (int l = 0; l < lanes; ++l) slabs.p[l] = wl[l].dth;
-  dtext_finalize_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, rnT, slabs, lanes, kDthSplits, Bt, D, dT);
+  dtext_finalize_kernel<<<Bt, 256, 0, st>>>(T, rnT, slabs, lanes, kDthSplits, Bt, D, dT);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
