@@ -230,6 +230,58 @@ def g5():
     return out
 
 
+def g7(pacl):
+    """Projection heads: the reference's own modules (pacl.py:35-48, :70-79) in eval mode with
+    seeded weights; the state dicts are stored so that the tests rebuild the same weights."""
+    import torch.nn as nn
+    torch.manual_seed(123)
+    Din, Dout = 128, 64
+    vis = nn.Sequential(nn.LayerNorm(Din), nn.Dropout(0.1), pacl.Patch_Projection(Din, Dout)).eval()
+    txt = nn.Sequential(nn.LayerNorm(Dout), nn.Dropout(0.1), nn.Linear(Dout, Dout)).eval()
+    with torch.no_grad():      # non-trivial LayerNorm affine parameters
+        vis[0].weight.copy_(1.0 + 0.1 * O.rn(31, Din)); vis[0].bias.copy_(0.1 * O.rn(32, Din))
+        txt[0].weight.copy_(1.0 + 0.1 * O.rn(33, Dout)); txt[0].bias.copy_(0.1 * O.rn(34, Dout))
+    x = O.rn(21, 3, 50, Din).requires_grad_()
+    t = O.rn(22, 5, Dout).requires_grad_()
+    gy, gt = O.rn(23, 3, 50, Dout), O.rn(24, 5, Dout)
+    y = vis(x)
+    ty = txt(t)
+    ((y * gy).sum() + (ty * gt).sum()).backward()
+    out = dict(vis_sd={k: v.detach().clone() for k, v in vis.state_dict().items()},
+               txt_sd={k: v.detach().clone() for k, v in txt.state_dict().items()},
+               y=y.detach().clone(), ty=ty.detach().clone(), dx=x.grad.clone(), dt=t.grad.clone(),
+               vis_grads={k: p.grad.clone() for k, p in vis.named_parameters()},
+               txt_grads={k: p.grad.clone() for k, p in txt.named_parameters()})
+    # oracle check
+    sd = {k: v.clone().requires_grad_() for k, v in out["vis_sd"].items()}
+    sdt = {k: v.clone().requires_grad_() for k, v in out["txt_sd"].items()}
+    x2 = O.rn(21, 3, 50, Din).requires_grad_()
+    t2 = O.rn(22, 5, Dout).requires_grad_()
+    y2, ty2 = O.visual_projection(x2, sd), O.text_projection(t2, sdt)
+    ((y2 * gy).sum() + (ty2 * gt).sum()).backward()
+    _close(y2.detach(), out["y"], what="G7 y")
+    _close(ty2.detach(), out["ty"], what="G7 ty")
+    _close(x2.grad, out["dx"], tol=5e-6, what="G7 dx")
+    _close(t2.grad, out["dt"], tol=5e-6, what="G7 dt")
+    for k, g in out["vis_grads"].items():
+        # linear_projection and text_projection are ONE module registered twice (pacl.py:39): named_parameters()
+        # lists it once, under the first name
+        _close(sd[k].grad if sd[k].grad is not None else torch.zeros_like(g), g, tol=5e-6, what=f"G7 vis grad {k}")
+    for k, g in out["txt_grads"].items():
+        _close(sdt[k].grad, g, tol=5e-6, what=f"G7 txt grad {k}")
+    return out
+
+
+def main_heads():
+    assert refload.available(), "reference not found; run in the build container"
+    torch.set_num_threads(8)
+    G = dict(meta=dict(torch=torch.__version__, note="projection heads: outputs of the unmodified reference, CPU fp32"),
+             G7=g7(refload.load_pacl()))
+    torch.save(G, os.path.join(OUT_DIR, "goldens_heads.pt"))
+    print("G7 |y|", float(G["G7"]["y"].norm()), "|dx|", float(G["G7"]["dx"].norm()),
+          "keys", sorted(G["G7"]["vis_sd"].keys()))
+
+
 def main():
     assert refload.available(), "reference not found; run in the build container"
     torch.manual_seed(0)
@@ -261,4 +313,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "heads":      # only the projection-head fixture (goldens_heads.pt)
+        main_heads()
+    else:
+        main()

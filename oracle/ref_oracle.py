@@ -211,3 +211,37 @@ def openclip_loss_ranks(imgs, txts, logit_scale, local_loss=True, usehardtext=Tr
 # ----------------------------------------------------------------------------
 def rn(seed, *shape, dtype=torch.float32):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)).to(dtype)
+
+
+# ----------------------------------------------------------------------------
+# Projection heads  (PACL/model/pacl.py:35-48, :70-79)   -- SURVEY §8f rank 1
+# ----------------------------------------------------------------------------
+def layer_norm(x, weight, bias, eps=1e-5):
+    """nn.LayerNorm(D) (pacl.py:71, :76): biased variance over the last dim, eps inside the sqrt."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * weight + bias
+
+
+def gelu_erf(z):
+    """nn.GELU() default (pacl.py:44): 0.5 z (1 + erf(z / sqrt 2))."""
+    return 0.5 * z * (1.0 + torch.erf(z * 0.7071067811865476))
+
+
+def patch_projection(x, sd, prefix=""):
+    """Patch_Projection.forward (pacl.py:47-48): linear_projection(x) + non_linear_projection(x), with
+    non_linear_projection = Linear -> GELU -> Linear (pacl.py:42-46).  `sd` holds the reference's state-dict keys."""
+    W1, b1 = sd[prefix + "linear_projection.0.weight"], sd[prefix + "linear_projection.0.bias"]
+    W2, b2 = sd[prefix + "non_linear_projection.0.weight"], sd[prefix + "non_linear_projection.0.bias"]
+    W3, b3 = sd[prefix + "non_linear_projection.2.weight"], sd[prefix + "non_linear_projection.2.bias"]
+    return x @ W1.T + b1 + gelu_erf(x @ W2.T + b2) @ W3.T + b3
+
+
+def visual_projection(x, sd):
+    """visual_projection = Sequential(LayerNorm, Dropout(0.1), Patch_Projection) in eval mode (pacl.py:70-74)."""
+    return patch_projection(layer_norm(x, sd["0.weight"], sd["0.bias"]), sd, "2.")
+
+
+def text_projection(x, sd):
+    """text_projection = Sequential(LayerNorm, Dropout(0.1), Linear) in eval mode (pacl.py:75-79)."""
+    return layer_norm(x, sd["0.weight"], sd["0.bias"]) @ sd["2.weight"].T + sd["2.bias"]

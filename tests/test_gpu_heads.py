@@ -1,0 +1,99 @@
+"""GPU parity: projection heads (PACL/model/pacl.py:35-48, :70-79) through the C ABI vs the oracle
+and the reference's own outputs (tests/golden/goldens_heads.pt).
+
+Tolerances (bf16 tensor-core path against the fp32 oracle): outputs 2e-2 relative L2 (bf16 activations and weights,
+two chained GEMMs), input / weight / bias gradients 3e-2 relative L2; LayerNorm statistics are fp32."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_g7():
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G7"]
+
+
+def test_heads_state_dict_keys_match_reference():
+    from clip_embeds_b200.heads import VisualProjection, TextProjection
+    G = _load_g7()
+    vis, txt = VisualProjection(128, 64), TextProjection(64)
+    assert sorted(vis.state_dict().keys()) == sorted(G["vis_sd"].keys())
+    assert sorted(txt.state_dict().keys()) == sorted(G["txt_sd"].keys())
+    vis.load_state_dict(G["vis_sd"])
+    txt.load_state_dict(G["txt_sd"])
+    assert vis[2].linear_projection[0].weight is vis[2].text_projection[0].weight      # one module, two names (pacl.py:39)
+
+
+def test_heads_golden_small():
+    """The reference's own outputs and gradients (eval mode, Din=128, Dout=64, 150 tokens / 5 texts)."""
+    from clip_embeds_b200.heads import VisualProjection, TextProjection
+    G = _load_g7()
+    vis, txt = VisualProjection(128, 64).cuda().eval(), TextProjection(64).cuda().eval()
+    vis.load_state_dict(G["vis_sd"])
+    txt.load_state_dict(G["txt_sd"])
+    x = O.rn(21, 3, 50, 128).cuda().requires_grad_()
+    t = O.rn(22, 5, 64).cuda().requires_grad_()
+    y, ty = vis(x), txt(t)
+    assert y.dtype == torch.bfloat16 and y.shape == (3, 50, 64)
+    ((y.float() * O.rn(23, 3, 50, 64).cuda()).sum() + (ty.float() * O.rn(24, 5, 64).cuda()).sum()).backward()
+    print(f"heads golden: y {rel_l2(y.float().cpu(), G['y']):.2e} ty {rel_l2(ty.float().cpu(), G['ty']):.2e} "
+          f"dx {rel_l2(x.grad.cpu(), G['dx']):.2e} dt {rel_l2(t.grad.cpu(), G['dt']):.2e}")
+    assert rel_l2(y.float().cpu(), G["y"]) < 2e-2 and rel_l2(ty.float().cpu(), G["ty"]) < 2e-2
+    assert rel_l2(x.grad.cpu(), G["dx"]) < 3e-2 and rel_l2(t.grad.cpu(), G["dt"]) < 3e-2
+    for k, p in vis.named_parameters():
+        print(f"  vis {k}: {rel_l2(p.grad.cpu(), G['vis_grads'][k]):.2e}")
+        assert rel_l2(p.grad.cpu(), G["vis_grads"][k]) < 3e-2, k
+    for k, p in txt.named_parameters():
+        assert rel_l2(p.grad.cpu(), G["txt_grads"][k]) < 3e-2, k
+
+
+@pytest.mark.parametrize("shape", [(2, 576, 1024, 768), (3, 196, 768, 512), (1, 257, 1408, 1024)])
+def test_visual_projection_vs_oracle(shape):
+    """ViT-L/14-336 (1024 -> 768), ViT-B/16 (768 -> 512) and EVA01-g (1408 -> 1024) head shapes, seeded weights, against
+    the fp32 oracle evaluated on the same fp32 inputs."""
+    from clip_embeds_b200.heads import VisualProjection
+    B, P, Din, Dout = shape
+    torch.manual_seed(7)
+    vis = VisualProjection(Din, Dout).eval()
+    with torch.no_grad():
+        vis[0].weight.copy_(1.0 + 0.1 * O.rn(31, Din))
+        vis[0].bias.copy_(0.1 * O.rn(32, Din))
+    sd = {k: v.detach().clone().requires_grad_() for k, v in vis.state_dict().items()}
+    x = O.rn(41, B, P, Din)
+    gy = O.rn(42, B, P, Dout)
+    xo = x.clone().requires_grad_()
+    yo = O.visual_projection(xo, sd)
+    (yo * gy).sum().backward()
+    vis = vis.cuda()
+    xg = x.cuda().requires_grad_()
+    y = vis(xg)
+    (y.float() * gy.cuda()).sum().backward()
+    errs = {"y": rel_l2(y.float().cpu(), yo.detach()), "dx": rel_l2(xg.grad.cpu(), xo.grad)}
+    for k, p in vis.named_parameters():
+        errs[k] = rel_l2(p.grad.cpu(), sd[k].grad)
+    print(f"visual projection {shape}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert errs["y"] < 2e-2
+    for k, v in errs.items():
+        assert v < 3e-2, (k, v)
+
+
+def test_heads_feed_scorer_end_to_end():
+    """heads -> all-pairs scorer -> InfoNCE, gradients reach every head parameter (the PACL training graph,
+    pacl.py:135-145 with the north_star all-pairs scores)."""
+    from clip_embeds_b200.heads import VisualProjection, TextProjection
+    from clip_embeds_b200.losses import PaclAllPairsLoss
+    torch.manual_seed(3)
+    B, P = 8, 64
+    vis, txt = VisualProjection(256, 128).cuda().eval(), TextProjection(128).cuda().eval()
+    patches = O.rn(51, B, P, 256).cuda()
+    text_cls = O.rn(52, B, 128).cuda()
+    loss = PaclAllPairsLoss(0.1)(vis(patches), txt(text_cls))
+    loss.backward()
+    assert torch.isfinite(loss)
+    for p in list(vis.parameters()) + list(txt.parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0

@@ -88,3 +88,22 @@ def test_g6_allpairs(goldens):
     loss.backward()
     assert abs(loss.item() - G["loss"].item()) < 2e-6
     assert rel_l2(V.grad, G["dV"]) < 1e-5 and rel_l2(T.grad, G["dT"]) < 1e-5
+
+
+def test_g7_projection_heads():
+    """Projection heads: the restatement reproduces the reference's own modules
+    (tests/golden/goldens_heads.pt, made by `python oracle/make_golden.py heads`)."""
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G7"]
+    sd = {k: v.clone().requires_grad_() for k, v in G["vis_sd"].items()}
+    sdt = {k: v.clone().requires_grad_() for k, v in G["txt_sd"].items()}
+    x = O.rn(21, 3, 50, 128).requires_grad_()
+    t = O.rn(22, 5, 64).requires_grad_()
+    y, ty = O.visual_projection(x, sd), O.text_projection(t, sdt)
+    ((y * O.rn(23, 3, 50, 64)).sum() + (ty * O.rn(24, 5, 64)).sum()).backward()
+    assert torch.allclose(y.detach(), G["y"], atol=2e-6) and torch.allclose(ty.detach(), G["ty"], atol=2e-6)
+    assert rel_l2(x.grad, G["dx"]) < 1e-5 and rel_l2(t.grad, G["dt"]) < 1e-5
+    for k, g in G["vis_grads"].items():
+        assert rel_l2(sd[k].grad, g) < 1e-5, k
+    for k, g in G["txt_grads"].items():
+        assert rel_l2(sdt[k].grad, g) < 1e-5, k
