@@ -5,9 +5,9 @@
 //   text_projection     PACL/model/pacl.py:75-79   LayerNorm(D) -> Dropout(0.1) -> Linear(D, D)
 //
 // Layout: tokens are rows.  xn = LN(x) bf16 [R, Din]; weights bf16 [out, in] (nn.Linear layout), biases fp32.
-//   fwd   Z = xn W2^T + b2, H = gelu(Z)      one CTA-pair GEMM, two TMA outputs (Z is kept for the backward)
+//   fwd   z = xn W2^T + b2, H = gelu(z), G' = gelu'(z)   one CTA-pair GEMM, two TMA outputs (G' is kept for the backward)
 //         Y = xn W1^T + H W3^T + (b1 + b3)   one CTA-pair GEMM over two operand pairs (K = Din, then K = Dout)
-//   bwd   dZ = (dY W3) * gelu'(Z)            GEMM with Z chunks arriving by TMA in the epilogue
+//   bwd   dZ = (dY W3) * G'                  GEMM with the G' chunks arriving by TMA in the epilogue
 //         dxn = dY W1 + dZ W2                two operand pairs
 //         dW1 = dY^T xn, dW2 = dZ^T xn, dW3 = dY^T H    split-K over token blocks into fp32 slabs + a reduction
 //         db1 = db3 = colsum(dY), db2 = colsum(dZ)
@@ -22,8 +22,9 @@ namespace epi {
 // Returns erf(x) and e = exp(-x^2) (the backward needs it for the Gaussian density).
 __device__ __forceinline__ float erf_as(float x, float& e) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  e = exp2f(-1.4426950408889634f * ax * ax);
+  float t, q = ax * ax * -1.4426950408889634f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));      // one MUFU each: the IEEE
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));                               // forms add fix-up code
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -32,15 +33,17 @@ __device__ __forceinline__ float erf_as(float x, float& e) {
   return copysignf(r, x);
 }
 
-// acc = xn W2^T; z = acc + b2 (bf16, second output), h = gelu(bf16(z)) (bf16, first output).
-// gelu is evaluated on the bf16-rounded z so that the backward (which reads the stored z) sees the same point.
+// acc = xn W2^T; z = acc + b2; first output h = gelu(z), second output g = gelu'(z) (both bf16):
+//   gelu(z) = 0.5 z (1 + erf(z / sqrt 2)),   gelu'(z) = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi)
+// erf and the Gaussian share one evaluation, so the derivative costs three more instructions here and turns the
+// backward's epilogue into a single multiply (the pre-activation itself is not needed again).
 struct BiasGelu2 {
   static constexpr bool kTmaOut = true;
   static constexpr bool kTmaOut2 = true;
   using Side = float;          // lane l holds bias[n + l]
   struct Params {
-    eng::OutDesc out;    // H [1][R][N]
-    eng::OutDesc out2;   // Z [1][R][N]
+    eng::OutDesc out;    // H  [1][R][N]
+    eng::OutDesc out2;   // G' [1][R][N]
     const float* bias;   // [N]
     int N;
   };
@@ -51,20 +54,15 @@ struct BiasGelu2 {
     const int lane = (int)ptx::lane_id();
     return (n + lane < p.N) ? __ldg(p.bias + n + lane) : 0.f;
   }
-  __device__ void chunk(int, int, int, float* v, const Side& b_l, const uint32_t*, float* z) {
+  __device__ void chunk(int, int, int, float* v, const Side& b_l, const uint32_t*, float* g) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float z0 = v[j] + __shfl_sync(0xffffffffu, b_l, j);
-      float z1 = v[j + 1] + __shfl_sync(0xffffffffu, b_l, j + 1);
-      bf16_round_pair(z0, z1);
-      float e0, e1;
-      const float f0 = erf_as(z0 * 0.70710678118654752f, e0);
-      const float f1 = erf_as(z1 * 0.70710678118654752f, e1);
-      z[j] = z0;
-      z[j + 1] = z1;
-      const float hz0 = 0.5f * z0, hz1 = 0.5f * z1;
-      v[j] = fmaf(hz0, f0, hz0);
-      v[j + 1] = fmaf(hz1, f1, hz1);
+    for (int j = 0; j < 32; ++j) {
+      const float z = v[j] + __shfl_sync(0xffffffffu, b_l, j);
+      float e;
+      const float f = erf_as(z * 0.70710678118654752f, e);
+      const float phi = fmaf(0.5f, f, 0.5f);                  // Phi(z)
+      v[j] = z * phi;
+      g[j] = fmaf(z * 0.3989422804014327f, e, phi);
     }
   }
   __device__ void tile_end(int, int, int, int, int) {}
@@ -93,15 +91,15 @@ struct BiasTma {
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
-// acc = dY W3 (= dH);  dZ = dH * gelu'(z),  gelu'(z) = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi)
-// z chunks arrive through TMA (kChunkIn), dZ leaves through TMA.
+// acc = dY W3 (= dH);  dZ = dH * gelu'(z): the derivative chunks (stored by the forward) arrive through TMA
+// (kChunkIn), dZ leaves through TMA.
 struct GeluBwdIn {
   static constexpr bool kTmaOut = true;
   static constexpr bool kChunkIn = true;
   using Side = float;          // unused (the chunk-in path needs a side type)
   struct Params {
     eng::OutDesc out;    // dZ
-    eng::OutDesc in;     // Z
+    eng::OutDesc in;     // G' = gelu'(z)
   };
   Params p;
   __device__ explicit GeluBwdIn(const Params& pp) : p(pp) {}
@@ -110,15 +108,8 @@ struct GeluBwdIn {
   __device__ void chunk(int, int, int, float* d, const Side&, const uint32_t* in, float*) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      const float z0 = __uint_as_float(in[j >> 1] << 16);
-      const float z1 = __uint_as_float(in[j >> 1] & 0xFFFF0000u);
-      float e0, e1;
-      const float f0 = erf_as(z0 * 0.70710678118654752f, e0);
-      const float f1 = erf_as(z1 * 0.70710678118654752f, e1);
-      const float g0 = fmaf(z0 * 0.3989422804014327f, e0, fmaf(0.5f, f0, 0.5f));
-      const float g1 = fmaf(z1 * 0.3989422804014327f, e1, fmaf(0.5f, f1, 0.5f));
-      d[j] *= g0;
-      d[j + 1] *= g1;
+      d[j] *= __uint_as_float(in[j >> 1] << 16);
+      d[j + 1] *= __uint_as_float(in[j >> 1] & 0xFFFF0000u);
     }
   }
   __device__ void tile_end(int, int, int, int, int) {}
@@ -198,31 +189,57 @@ __global__ void ln_fwd_kernel(const T* __restrict__ X, int64_t rows, int D, cons
   }
 }
 
-// Column sums for d gamma / d beta (and plain column sums when X == nullptr), stage 1: block (bx, by) sums rows
-// [by * rows_per_block, ...) of columns [bx * 256, bx * 256 + 256) into part[by][{0,1}][D].
-//   dg[d] = sum_r G[r,d] * (x[r,d] - mean_r) rstd_r      db[d] = sum_r G[r,d]
+// Column sums for d gamma / d beta (and plain column sums when X == nullptr), stage 1.  Block (bx, by): columns
+// [256 bx, 256 bx + 256) of rows [by * rows_per_block, ...); every lane owns 8 consecutive columns (one 16-byte load
+// per row), a warp reads 512 contiguous bytes per row, eight rows in flight per block; part[by][{0,1}][D] receives
+// the block's sums.      dg[d] = sum_r G[r,d] * (x[r,d] - mean_r) rstd_r      db[d] = sum_r G[r,d]      (D % 8 == 0)
 template <typename T>
-__global__ void colsum_part_kernel(const __nv_bfloat16* __restrict__ G, const T* __restrict__ X,
-                                   const float* __restrict__ mean, const float* __restrict__ rstd, int64_t rows, int D,
-                                   int rows_per_block, float* __restrict__ part) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* __restrict__ G, const T* __restrict__ X,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          int64_t rows, int D, int rows_per_block,
+                                                          float* __restrict__ part) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = blockIdx.x * 256 + 8 * lane;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  if (d >= D) return;
-  float sg = 0.f, sb = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    const float g = __bfloat162float(G[r * D + d]);
-    sb += g;
-    if (X != nullptr) {
-      float xv;
-      if constexpr (sizeof(T) == 2) xv = __bfloat162float(X[r * D + d]);
-      else xv = X[r * D + d];
-      sg = fmaf(g, (xv - __ldg(mean + r)) * __ldg(rstd + r), sg);
+  float sg[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sg[i] = sb[i] = 0.f;
+  if (d < D) {
+#pragma unroll 4
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      float g[8];
+      load8<__nv_bfloat16>(G + r * D + d, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sb[i] += g[i];
+      if (X != nullptr) {
+        float x[8];
+        load8<T>(X + r * D + d, x);
+        const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sg[i] = fmaf(g[i], (x[i] - mu) * rs, sg[i]);
+      }
     }
   }
-  float* p = part + (int64_t)blockIdx.y * 2 * D;
-  p[d] = sg;
-  p[D + d] = sb;
+  float* out = part + (int64_t)blockIdx.y * 2 * D;
+  for (int pass = 0; pass < 2; ++pass) {        // pass 0: dg, pass 1: db  (cross-warp sums in a fixed order)
+    if (pass == 0 && X == nullptr) {
+      if (blockIdx.x * 256 + threadIdx.x < D) out[blockIdx.x * 256 + threadIdx.x] = 0.f;
+      continue;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][8 * lane + i] = pass == 0 ? sg[i] : sb[i];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+      out[pass * D + c] = t;
+    }
+  }
 }
 // stage 2: out_g[d] = sum_by part[by][0][d], out_b[d] = sum_by part[by][1][d]  (fixed order: deterministic)
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nblk, int D, float* __restrict__ out_g,
@@ -287,7 +304,7 @@ __global__ void slab_reduce_kernel(const float4* __restrict__ slabs, int nslab, 
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-constexpr int kColsumRowsPerBlock = 1024;
+constexpr int kColsumRowsPerBlock = 4096;
 static inline int colsum_blocks(int64_t rows) { return (int)((rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock); }
 
 template <typename T>
@@ -441,9 +458,10 @@ int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gam
 }
 
 // Patch_Projection forward (pacl.py:35-48).  xn bf16 [R, Din]; W1, W2 bf16 [Dout, Din]; W3 bf16 [Dout, Dout];
-// b13 = b1 + b3, b2: fp32 [Dout].  Outputs (bf16 [R, Dout]): Z (pre-activation), H = gelu(Z), Y.
+// b13 = b1 + b3, b2: fp32 [Dout].  Outputs (bf16 [R, Dout]): Gp = gelu'(z), H = gelu(z) (both saved for the
+// backward), Y.
 int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const void* W1, const void* W2, const void* W3,
-                         const float* b13, const float* b2, void* Z, void* H, void* Y, void* stream) {
+                         const float* b13, const float* b2, void* Gp, void* H, void* Y, void* stream) {
   using namespace clipk;
   CLIPK_TRY(check_device());
   CLIPK_TRY(check_rows(R));
@@ -455,7 +473,7 @@ int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const voi
     a.ptr = xn; a.rows = M; a.k = Din; a.ld = Din;
     b.ptr = W2; b.rows = Dout; b.k = Din; b.ld = Din;
     const int ks[1] = {(Din + 63) / 64};
-    const eng::OutDesc oh{H, Dout, (int64_t)M * Dout, M, Dout, 1}, oz{Z, Dout, (int64_t)M * Dout, M, Dout, 1};
+    const eng::OutDesc oh{H, Dout, (int64_t)M * Dout, M, Dout, 1}, oz{Gp, Dout, (int64_t)M * Dout, M, Dout, 1};
     epi::BiasGelu2::Params ep{oh, oz, b2, Dout};
     CLIPK_TRY((launch_gemm2<256, false, false, epi::BiasGelu2>(&a, &b, 1, ks, ks, M, Dout, 1, ep, st)));
   }
@@ -479,7 +497,7 @@ size_t clipk_patch_proj_bwd_workspace_bytes(int64_t R, int Din, int Dout) {
 
 // Patch_Projection backward.  dY bf16 [R, Dout].  dxn (nullable) bf16 [R, Din]; dW1, dW2 [Dout, Din], dW3 [Dout, Dout],
 // db13 (= db1 = db3), db2 [Dout]: fp32, overwritten.
-int clipk_patch_proj_bwd(const void* xn, const void* Z, const void* H, const void* dY, int64_t R, int Din, int Dout,
+int clipk_patch_proj_bwd(const void* xn, const void* Gp, const void* H, const void* dY, int64_t R, int Din, int Dout,
                          const void* W1, const void* W2, const void* W3, void* dxn, float* dW1, float* dW2, float* dW3,
                          float* db13, float* db2, void* workspace, size_t ws_bytes, void* stream) {
   using namespace clipk;
@@ -493,14 +511,14 @@ int clipk_patch_proj_bwd(const void* xn, const void* Z, const void* H, const voi
   const int M = (int)R;
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dY);
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(xn);
-  // dZ = (dY W3) * gelu'(Z)        B[n][k] = W3[k][n]: W3 read as an MN-major operand
+  // dZ = (dY W3) * G'        B[n][k] = W3[k][n]: W3 read as an MN-major operand
   {
     OperandDesc a, b;
     a.ptr = dY; a.rows = M; a.k = Dout; a.ld = Dout;
     b.ptr = W3; b.mn_major = true; b.rows = Dout; b.k = Dout; b.ld = Dout;
     const int ks[1] = {(Dout + 63) / 64};
     const eng::OutDesc od{w.dZ, Dout, (int64_t)M * Dout, M, Dout, 1};
-    const eng::OutDesc oz{const_cast<void*>(Z), Dout, (int64_t)M * Dout, M, Dout, 1};
+    const eng::OutDesc oz{const_cast<void*>(Gp), Dout, (int64_t)M * Dout, M, Dout, 1};
     epi::GeluBwdIn::Params ep{od, oz};
     if (Dout > 128) CLIPK_TRY((launch_gemm2<256, false, true, epi::GeluBwdIn>(&a, &b, 1, ks, ks, M, Dout, 1, ep, st)));
     else CLIPK_TRY((launch_gemm2<128, false, true, epi::GeluBwdIn>(&a, &b, 1, ks, ks, M, Dout, 1, ep, st)));

@@ -78,19 +78,19 @@ class _PatchProj(torch.autograd.Function):
         w1, w2, w3 = (w.detach().to(torch.bfloat16).contiguous() for w in (W1, W2, W3))
         b13 = (b1.detach().float() + b3.detach().float()).contiguous()
         b2f = b2.detach().float().contiguous()
-        Z = torch.empty(R, Dout, dtype=torch.bfloat16, device=dev)
-        H = torch.empty_like(Z)
-        Y = torch.empty_like(Z)
+        Gp = torch.empty(R, Dout, dtype=torch.bfloat16, device=dev)      # gelu'(z), saved for the backward
+        H = torch.empty_like(Gp)
+        Y = torch.empty_like(Gp)
         _lib.call("clipk_patch_proj_fwd", x2.data_ptr(), R, Din, Dout, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(),
-                  b13.data_ptr(), b2f.data_ptr(), Z.data_ptr(), H.data_ptr(), Y.data_ptr(), _stream())
-        ctx.save_for_backward(x2, Z, H, w1, w2, w3)
+                  b13.data_ptr(), b2f.data_ptr(), Gp.data_ptr(), H.data_ptr(), Y.data_ptr(), _stream())
+        ctx.save_for_backward(x2, Gp, H, w1, w2, w3)
         ctx.lead = lead
         ctx.dts = tuple(t.dtype for t in (xn, W1, b1, W2, b2, W3, b3))
         return Y.reshape(*lead, Dout)
 
     @staticmethod
     def backward(ctx, dY):
-        x2, Z, H, w1, w2, w3 = ctx.saved_tensors
+        x2, Gp, H, w1, w2, w3 = ctx.saved_tensors
         R, Din = x2.shape
         Dout = w1.shape[0]
         dev = x2.device
@@ -101,7 +101,7 @@ class _PatchProj(torch.autograd.Function):
         db13, db2 = _f32(Dout, device=dev), _f32(Dout, device=dev)
         nbytes = _lib.lib().clipk_patch_proj_bwd_workspace_bytes(R, Din, Dout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.call("clipk_patch_proj_bwd", x2.data_ptr(), Z.data_ptr(), H.data_ptr(), dy.data_ptr(), R, Din, Dout,
+        _lib.call("clipk_patch_proj_bwd", x2.data_ptr(), Gp.data_ptr(), H.data_ptr(), dy.data_ptr(), R, Din, Dout,
                   w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), 0 if dxn is None else dxn.data_ptr(), dW1.data_ptr(),
                   dW2.data_ptr(), dW3.data_ptr(), db13.data_ptr(), db2.data_ptr(), ws.data_ptr(), nbytes, _stream())
         dt = ctx.dts

@@ -187,8 +187,9 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
  *   clipk_ln_fwd : xn = (x - mean) rstd gamma + beta, saves mean / rstd (biased variance, eps inside the sqrt)
  *   clipk_ln_bwd : dgamma, dbeta [D] from dxn (bf16); dx (nullable; dtype of x) = gradient wrt the LayerNorm input
  * Patch_Projection: y = W1 xn + b1 + W3 gelu(W2 xn + b2) + b3 (erf GELU).  Weights bf16 [out, in], biases fp32,
- * b13 = b1 + b3.  fwd writes Z (pre-activation), H = gelu(Z), Y (all bf16 [R, Dout]); bwd consumes dY (bf16) and
- * writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
+ * b13 = b1 + b3.  fwd writes Gp = gelu'(z), H = gelu(z) (saved for the backward) and Y (all bf16 [R, Dout]); bwd
+ * consumes dY (bf16) and
+ writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
  * clipk_linear_*: y = x W^T + b on bf16 rows, dx (nullable) bf16, dW / db fp32. */
 int clipk_ln_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta, float eps,
                  void* xn, float* mean, float* rstd, void* stream);
@@ -197,9 +198,9 @@ int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gam
                  const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, void* workspace,
                  size_t ws_bytes, void* stream);
 int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const void* W1, const void* W2, const void* W3,
-                         const float* b13, const float* b2, void* Z, void* H, void* Y, void* stream);
+                         const float* b13, const float* b2, void* Gp, void* H, void* Y, void* stream);
 size_t clipk_patch_proj_bwd_workspace_bytes(int64_t R, int Din, int Dout);
-int clipk_patch_proj_bwd(const void* xn, const void* Z, const void* H, const void* dY, int64_t R, int Din, int Dout,
+int clipk_patch_proj_bwd(const void* xn, const void* Gp, const void* H, const void* dY, int64_t R, int Din, int Dout,
                          const void* W1, const void* W2, const void* W3, void* dxn, float* dW1, float* dW2, float* dW3,
                          float* db13, float* db2, void* workspace, size_t ws_bytes, void* stream);
 int clipk_linear_fwd(const void* x, int64_t R, int Din, int Dout, const void* W, const float* bias, void* y,
