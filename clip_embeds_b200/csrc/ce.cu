@@ -406,7 +406,7 @@ struct DlOutTma {
     // w (exp(logit - lse) - [n + j == label]);  rows with w == 0 (ignored rows, rows past M) give exact zeros
     const float k2 = p.scale * 1.4426950408889634f, c2 = nlse * 1.4426950408889634f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (w == 0.f) ? 0.f : w * exp2f(fmaf(v[j], k2, c2));
+    for (int j = 0; j < 32; ++j) v[j] = (w == 0.f) ? 0.f : w * ptx::ex2_approx(fmaf(v[j], k2, c2));
     const int rel = lab - n;
     if (rel >= 0 && rel < 32) {
 #pragma unroll

@@ -247,7 +247,7 @@ struct PaclAct {
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = __shfl_sync(0xffffffffu, rn_l, j0 + i);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = exp2f(fmaf(v[j0 + i] * k2, r[i], -14.426950408889634f));
+        for (int i = 0; i < 8; ++i) a[i] = ptx::ex2_approx(fmaf(v[j0 + i] * k2, r[i], -14.426950408889634f));
 #pragma unroll
         for (int i = 0; i < 8; i += 2) bf16_round_pair(a[i], a[i + 1]);
 #pragma unroll
@@ -369,7 +369,7 @@ struct PaclActS {
       for (int j = 0; j < 32; ++j) {
         const float r0 = __shfl_sync(0xffffffffu, rn_l, j);
         x[j] = v[j] * rt;
-        v[j] = exp2f(fmaf(v[j] * k2, r0, -14.426950408889634f));
+        v[j] = ptx::ex2_approx(fmaf(v[j] * k2, r0, -14.426950408889634f));
       }
       return;
     }
@@ -434,8 +434,8 @@ struct DsIn {
         const float x0 = __uint_as_float(in[j >> 1] << 16);
         const float x1 = __uint_as_float(in[j >> 1] & 0xFFFF0000u);
         const float s0 = x0 * r0, s1 = x1 * r1;
-        float a0 = exp2f(14.426950408889634f * (s0 - 1.f));
-        float a1 = exp2f(14.426950408889634f * (s1 - 1.f));
+        float a0 = ptx::ex2_approx(14.426950408889634f * (s0 - 1.f));
+        float a1 = ptx::ex2_approx(14.426950408889634f * (s1 - 1.f));
         bf16_round_pair(a0, a1);
         const float ds0 = fmaf(al, x0, d[j]) * g10 * a0;
         const float ds1 = fmaf(al, x1, d[j + 1]) * g10 * a1;

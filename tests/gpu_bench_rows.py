@@ -4,7 +4,7 @@ restatement of the reference (the oracle, run on the same GPU), with the §8d al
     python tests/gpu_bench_rows.py [--json out.json]
 
 Diagnostic companion of bench.py (which measures the BASELINE.json headline metric only); results are copied into
-DESIGN.md / profiles/.  Timing: CUDA events, 3 warm-ups, median of 7.
+DESIGN.md / profiles/.  Timing: CUDA events around 7 back-to-back calls, 3 warm-ups, best of 3.
 """
 import json
 import os
@@ -33,19 +33,22 @@ def on_gpu(fn):
     return run
 
 
-def timed(fn, warm=3, iters=7):
+def timed(fn, warm=3, iters=7, reps=3):
+    """ms per call: `iters` calls back to back between two CUDA events (as a training loop issues them, so that host
+    launch overhead overlaps device work), best of `reps`."""
     for _ in range(warm):
         fn()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
+    best = float("inf")
+    for _ in range(reps):
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(iters):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return statistics.median(ts)
+        best = min(best, e0.elapsed_time(e1) / iters)
+    return best
 
 
 def row(name, ours_ms, ref_ms, units, unit_name, gbytes=None, tflop=None):
@@ -105,7 +108,7 @@ def main():
             (100.0 * img @ txt.T).diagonal()
 
     out.append(row("a3 eval scorer, 2247 items x 2 captions, fp32 (eager ref: per-item loop)", timed(ours_eval),
-                   timed(on_gpu(ref_eval), 1, 3), items, "items", gbytes=items * P * D * 4 / 1e9))
+                   timed(on_gpu(ref_eval), 1, 2, 2), items, "items", gbytes=items * P * D * 4 / 1e9))
     del Ve, Te
 
     # ---- a4: PACL ClipLoss at the reference training batch (B=4096), bf16 features
@@ -184,6 +187,42 @@ def main():
     flop = 6.0 * (b * (N + H) + (b + H // 8) * N) * D / 1e12
     out.append(row("a8 NegCLIP local-loss rank share (W=8 of C4): [4096 x 40960] + [5120 x 32768] logits, D=768, bf16 "
                    "(eager ref: fp32 TF32-off)", timed(ours_neg), timed(on_gpu(ref_neg)), b, "pairs", tflop=flop))
+    del img_loc, txt_all, txt_loc, img_all, fl
+
+    # ---- f1: visual projection head LayerNorm -> Patch_Projection(1024 -> 768), fwd+bwd, 1024 x 576 tokens
+    import torch.nn as nn
+    from clip_embeds_b200.heads import VisualProjection
+    Bh, Din, Dout = 1024, 1024, 768
+    torch.manual_seed(0)
+    vis = VisualProjection(Din, Dout).to(dev).eval()
+    xh = torch.randn(Bh, P, Din, device=dev).to(torch.bfloat16)
+    gyh = torch.randn(Bh, P, Dout, device=dev).to(torch.bfloat16)
+
+    def ours_heads():
+        for p_ in vis.parameters():
+            p_.grad = None
+        vis(xh).backward(gyh)
+
+    class _PP(nn.Module):          # the reference's Patch_Projection structure (pacl.py:35-48) in eager torch, bf16 weights
+        def __init__(self):
+            super().__init__()
+            self.l = nn.Linear(Din, Dout)
+            self.n = nn.Sequential(nn.Linear(Din, Dout), nn.GELU(), nn.Linear(Dout, Dout))
+
+        def forward(self, z):
+            return self.l(z) + self.n(z)
+
+    refh = nn.Sequential(nn.LayerNorm(Din), nn.Dropout(0.1), _PP()).to(dev).to(torch.bfloat16).eval()
+
+    def ref_heads():
+        for p_ in refh.parameters():
+            p_.grad = None
+        refh(xh).backward(gyh)
+
+    Rt = Bh * P
+    flop_h = 2.0 * Rt * (2 * Din * Dout + Dout * Dout) * 3 / 1e12       # fwd + (dgrad + wgrad)
+    out.append(row("f1 visual projection head (LayerNorm + Patch_Projection 1024->768) fwd+bwd, 1024x576 tokens, bf16 "
+                   "(eager ref: bf16 cuBLAS)", timed(ours_heads), timed(ref_heads), Bh, "images", tflop=flop_h))
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
             json.dump({"peaks": PEAKS, "rows": out}, f, indent=1)
