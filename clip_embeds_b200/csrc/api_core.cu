@@ -44,6 +44,17 @@ void trace_end(cudaStream_t st) {
   if (!g_trace.empty()) cudaEventRecord(g_trace.back().e1, st);
 }
 
+static thread_local int g_pdl_block = 0;
+PdlBlock::PdlBlock(bool block) : active(block) { if (active) ++g_pdl_block; }
+PdlBlock::~PdlBlock() { if (active) --g_pdl_block; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPK_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on && g_pdl_block == 0;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

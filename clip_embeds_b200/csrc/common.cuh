@@ -19,6 +19,17 @@ void set_error(const char* fmt, ...);          // thread-local message returned 
 int check_device();                            // 0 if the current device is sm_100 (B200), else CLIPK_ERR_ARCH
 int sm_count();                                // SM count of the current device
 void count_launches(int n);
+bool pdl_enabled();                            // CLIPK_PDL=0 disables programmatic dependent launch of the CTA-pair engine
+// Scope guard: no programmatic dependent launch on this thread while it lives.  Used where several stream lanes feed
+// the GPU: a dependent grid's CTAs would take freed SMs only to wait, ahead of the other lane's runnable CTAs
+// (measured: 64-image groups on 2 lanes 8.0-8.4 ms without, 8.6 ms with).
+struct PdlBlock {
+  bool active;
+  explicit PdlBlock(bool block);
+  ~PdlBlock();
+  PdlBlock(const PdlBlock&) = delete;
+  PdlBlock& operator=(const PdlBlock&) = delete;
+};
 bool trace_enabled();                          // CLIPK_TRACE=1: record CUDA events around every engine launch
 void trace_begin(const char* name, cudaStream_t st);
 void trace_end(cudaStream_t st);                    // bump the library-wide kernel-launch counter (clipk_launch_count)
@@ -208,7 +219,22 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
   const int grid = 2 * (total < pairs ? total : pairs);
   const bool tr = trace_enabled();
   if (tr) trace_begin(__PRETTY_FUNCTION__, stream);
-  kern<<<grid, eng2::threads_for(kEpiWarps), L::kTotal, stream>>>(maps, pb, ep);
+  if (pdl_enabled()) {
+    // programmatic dependent launch: the next engine kernel's prologue overlaps this kernel's tail (see the kernel)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(eng2::threads_for(kEpiWarps));
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CLIPK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, pb, ep));
+  } else {
+    kern<<<grid, eng2::threads_for(kEpiWarps), L::kTotal, stream>>>(maps, pb, ep);
+  }
   if (tr) trace_end(stream);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());

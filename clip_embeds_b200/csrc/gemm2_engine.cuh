@@ -167,6 +167,12 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   ptx::cluster_sync_all();       // barriers initialised and TMEM allocated in BOTH CTAs before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster sync) may overlap the tail
+  // of the previous kernel in the stream; nothing below may start before that kernel has completed and flushed.
+  // The dependents of THIS kernel may be scheduled as soon as every CTA has got here (they block at the same point).
+  // Both instructions are no-ops when the launch carries no programmatic-serialisation attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)

@@ -485,6 +485,7 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
   LanePool* lp = nullptr;
+  const PdlBlock no_pdl(lanes > 1);
   if (lanes > 1) {
     CLIPK_TRY(get_lanes(&lp));
     CLIPK_TRY(fork_lanes(lp, lanes, st));
@@ -530,6 +531,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
   count_launches(2);
   LanePool* lp = nullptr;
+  const PdlBlock no_pdl(lanes > 1);
   if (lanes > 1) {
     CLIPK_TRY(get_lanes(&lp));
     CLIPK_TRY(fork_lanes(lp, lanes, st));
