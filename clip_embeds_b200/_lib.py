@@ -66,6 +66,9 @@ SIGNATURES = {
     "clipk_linear_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "clipk_linear_bwd_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
     "clipk_linear_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "clipk_eval_correct": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    "clipk_eval_whatsup": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "clipk_eval_mmvp": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

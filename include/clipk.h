@@ -209,6 +209,20 @@ size_t clipk_linear_bwd_workspace_bytes(int64_t R, int Din, int Dout);
 int clipk_linear_bwd(const void* x, const void* dY, int64_t R, int Din, int Dout, const void* W, void* dx, float* dW,
                      float* db, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Batched eval protocol: the accuracy accounting of PACL/eval_pacl.py on the device, fed by the
+ * one-launch scorer (clipk_pacl_paired_fwd with v_div = K).
+ *   clipk_eval_correct : correct[i] = score[i,0] > score[i,k] for all k > 0           (eval_pacl.py:53-57, :130-134)
+ *   clipk_eval_whatsup : individual / pair / set counts over (set_id, rel_id) keys      (eval_pacl.py:59-104)
+ *                        rel_id: 0 left, 1 right, 2 on, 3 under, 4 in-front, 5 behind; a later item with the same
+ *                        key overwrites an earlier one; counts[8] = indiv lr/ou/fb, pair lr/ou/fb, sets, items
+ *   clipk_eval_mmvp    : pairs of (2 images x 2 texts): pred / pair / single counts per category (eval_pacl.py:303-335) */
+int clipk_eval_correct(const float* scores, int items, int K, int* correct, void* stream);
+int clipk_eval_whatsup(const int* correct, const int* set_id, const int* rel_id, int items, int nsets, int* winner_ws,
+                       int* counts, void* stream);
+int clipk_eval_mmvp(const float* s_img1, const float* s_img2, const int* gt, int pairs, int pairs_per_cat, int ncat,
+                    int* pred, int* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,3 +245,53 @@ def visual_projection(x, sd):
 def text_projection(x, sd):
     """text_projection = Sequential(LayerNorm, Dropout(0.1), Linear) in eval mode (pacl.py:75-79)."""
     return layer_norm(x, sd["0.weight"], sd["0.bias"]) @ sd["2.weight"].T + sd["2.bias"]
+
+
+# ----------------------------------------------------------------------------
+# Eval protocol accounting  (PACL/eval_pacl.py)   -- SURVEY §8f rank 2
+# ----------------------------------------------------------------------------
+_RELS = ("left", "right", "on", "under", "in-front", "behind")
+
+
+def whatsup_accounting(scores, set_id, rel_id):
+    """eval_pacl.py:53-104 on precomputed diagonal scores [items,K]: `correct` is the strict comparison of caption 0
+    against every other caption (:56, :133); eval_dict[(object pair)][relation] = correct (:59-60, later items
+    overwrite); individual / pair / set counts (:63-85).  Returns (counts [ind_lr, ind_ou, ind_fb, pair_lr, pair_ou,
+    pair_fb, sets, total], correct list).  Parity: restated from the script (it needs the datasets and a model to
+    run), not pinned by a reference output."""
+    items, K = scores.shape
+    correct = [int(all(bool(scores[i, 0] > scores[i, k]) for k in range(1, K))) for i in range(items)]
+    eval_dict = {}
+    for i in range(items):
+        eval_dict.setdefault(int(set_id[i]), {r: 0 for r in _RELS})[_RELS[int(rel_id[i])]] = correct[i]
+    ind = [0, 0, 0]
+    pair = [0, 0, 0]
+    sets = 0
+    for d in eval_dict.values():
+        for g, (a, b) in enumerate((("left", "right"), ("under", "on"), ("behind", "in-front"))):
+            if d[a] and d[b]:
+                pair[g] += 1
+            ind[g] += d[a] + d[b]
+        if sum(d.values()) == 4:
+            sets += 1
+    return ind + pair + [sets, items], correct
+
+
+def mmvp_accounting(s1, s2, gt, pairs_per_cat=0, ncat=1):
+    """eval_pacl.py:303-335 on precomputed diagonal scores s1, s2 [pairs,2] (image 1 / image 2 against the two
+    statements): logits_per_text rows = statements, softmax over the two images (fp32), pred = img1 iff prob > 0.5;
+    returns ([[pair, single] per category], pred [pairs,2])."""
+    pairs = s1.shape[0]
+    counts = [[0, 0] for _ in range(ncat)]
+    pred = torch.zeros(pairs, 2, dtype=torch.int32)
+    for i in range(pairs):
+        logits_per_text = torch.tensor([[s1[i, 0], s1[i, 1]], [s2[i, 0], s2[i, 1]]]).float().T
+        ok = 0
+        for t in range(2):
+            p = int(logits_per_text[t].softmax(dim=-1)[0] > 0.5)
+            pred[i, t] = p
+            ok += int(p == int(gt[i, t] != 0))
+        cat = min(i // pairs_per_cat, ncat - 1) if pairs_per_cat > 0 else 0
+        counts[cat][0] += int(ok == 2)
+        counts[cat][1] += ok
+    return counts, pred

@@ -109,6 +109,25 @@ def main():
 
     out.append(row("a3 eval scorer, 2247 items x 2 captions, fp32 (eager ref: per-item loop)", timed(ours_eval),
                    timed(on_gpu(ref_eval), 1, 2, 2), items, "items", gbytes=items * P * D * 4 / 1e9))
+    # ---- f2: the same set through the whole protocol (scores + accuracy accounting on the device)
+    from clip_embeds_b200 import evalproto
+    set_id = torch.arange(items) // 4
+    rel_id = torch.arange(items) % 4
+
+    def ours_proto():
+        evalproto.whatsup_accuracies(Ve, Te, set_id, rel_id)
+
+    def ref_proto():      # eval_pacl.py:38-104: per-item forward, host comparison (.item() sync per item), dict bookkeeping
+        sc = []
+        for i in range(items):
+            img, txt = O.pacl_forward(Ve[i:i + 1].expand(K, P, D), Te[i], "sigmoid")
+            pr = 100.0 * img @ txt.T
+            sc.append([float(pr[0][0]), float(pr[1][1])])
+        O.whatsup_accounting(torch.tensor(sc), set_id, rel_id)
+
+    out.append(row("f2 What'sUp protocol end to end (scores + individual/pair/set accuracies), 2247 items x 2 captions, fp32 "
+                   "(eager ref: per-item loop + host bookkeeping)", timed(ours_proto), timed(on_gpu(ref_proto), 1, 1, 2),
+                   items, "items", gbytes=items * P * D * 4 / 1e9))
     del Ve, Te
 
     # ---- a4: PACL ClipLoss at the reference training batch (B=4096), bf16 features
