@@ -303,6 +303,39 @@ __global__ void slab_reduce_kernel(const float4* __restrict__ slabs, int nslab, 
   out[i] = a;
 }
 
+// ---------------------------------------------------------------------------------------------- RoPE
+// apply_rope (PACL/model/pacl.py:147-181): position p = row % S, pair j = (x[2j], x[2j+1]), angle table [S][D/2]:
+//   out[j] = x[2j] cos - x[2j+1] sin,   out[D/2 + j] = x[2j] sin + x[2j+1] cos        (de-interleave, then concat halves)
+// INVERSE != 0 applies the transpose (the gradient): dx[2j] = g[j] cos + g[D/2+j] sin, dx[2j+1] = -g[j] sin + g[D/2+j] cos.
+template <typename TI, typename TO, bool INVERSE>
+__global__ void rope_kernel(const TI* __restrict__ X, int64_t rows, int S, int D, const float* __restrict__ sn,
+                            const float* __restrict__ cs, TO* __restrict__ Y) {
+  const int half = D >> 1;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one (row, pair) per thread
+  if (idx >= rows * half) return;
+  const int64_t row = idx / half;
+  const int j = (int)(idx - row * half);
+  const int p = (int)(row % S);
+  const float s = __ldg(sn + (int64_t)p * half + j), c = __ldg(cs + (int64_t)p * half + j);
+  auto ld = [&](int64_t i) -> float {
+    if constexpr (sizeof(TI) == 2) return __bfloat162float(X[i]);
+    else return X[i];
+  };
+  auto st = [&](int64_t i, float v) {
+    if constexpr (sizeof(TO) == 2) Y[i] = __float2bfloat16(v);
+    else Y[i] = v;
+  };
+  if constexpr (!INVERSE) {
+    const float x1 = ld(row * D + 2 * j), x2 = ld(row * D + 2 * j + 1);
+    st(row * D + j, x1 * c - x2 * s);
+    st(row * D + half + j, x1 * s + x2 * c);
+  } else {
+    const float g1 = ld(row * D + j), g2 = ld(row * D + half + j);
+    st(row * D + 2 * j, g1 * c + g2 * s);
+    st(row * D + 2 * j + 1, g2 * c - g1 * s);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 constexpr int kColsumRowsPerBlock = 4096;
 static inline int colsum_blocks(int64_t rows) { return (int)((rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock); }
@@ -453,6 +486,39 @@ int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gam
                                                     static_cast<float*>(dx));
   }
   if (dx != nullptr) count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// apply_rope (pacl.py:147-181) on rows of [B*S, D]; sin / cos: fp32 [S, D/2] (built by the caller exactly as the
+// reference does).  dtype_in / dtype_out: bf16 | fp32.  inverse != 0: the transposed rotation (gradient).
+int clipk_rope(const void* x, int dtype_in, int64_t rows, int S, int D, const float* sin_t, const float* cos_t, void* y,
+               int dtype_out, int inverse, void* stream) {
+  using namespace clipk;
+  CLIPK_TRY(check_device());
+  CLIPK_REQUIRE(rows >= 0 && S > 0 && D > 0 && D % 2 == 0, "rope: bad shape rows=%lld S=%d D=%d (D even)", (long long)rows, S, D);
+  CLIPK_REQUIRE((dtype_in == CLIPK_BF16 || dtype_in == CLIPK_F32) && (dtype_out == CLIPK_BF16 || dtype_out == CLIPK_F32),
+                "rope: dtypes must be bf16 or fp32");
+  if (rows == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = rows * (D / 2);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+#define CLIPK_ROPE(TI, TO, INV) \
+  rope_kernel<TI, TO, INV><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), rows, S, D, sin_t, cos_t, static_cast<TO*>(y))
+  const bool ib = dtype_in == CLIPK_BF16, ob = dtype_out == CLIPK_BF16;
+  if (!inverse) {
+    if (ib && ob) CLIPK_ROPE(__nv_bfloat16, __nv_bfloat16, false);
+    else if (ib) CLIPK_ROPE(__nv_bfloat16, float, false);
+    else if (ob) CLIPK_ROPE(float, __nv_bfloat16, false);
+    else CLIPK_ROPE(float, float, false);
+  } else {
+    if (ib && ob) CLIPK_ROPE(__nv_bfloat16, __nv_bfloat16, true);
+    else if (ib) CLIPK_ROPE(__nv_bfloat16, float, true);
+    else if (ob) CLIPK_ROPE(float, __nv_bfloat16, true);
+    else CLIPK_ROPE(float, float, true);
+  }
+#undef CLIPK_ROPE
+  count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

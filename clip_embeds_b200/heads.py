@@ -186,3 +186,54 @@ class TextProjection(nn.Sequential):
         if self.training and drop.p > 0:
             xn = torch.nn.functional.dropout(xn, drop.p, True)
         return _Linear.apply(xn, lin.weight, lin.bias)
+
+
+# ------------------------------------------------------------------------------------------------ RoPE (§8f rank 3)
+_ROPE_TABLES = {}
+
+
+def _rope_tables(S, D, device):
+    """sin / cos [S, D/2] fp32, computed on the CPU with the reference's own expressions (pacl.py:160-171) so that the
+    angles are bit-identical, cached per (S, D, device)."""
+    key = (S, D, str(device))
+    if key not in _ROPE_TABLES:
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))
+        angles = torch.arange(S, dtype=torch.float).unsqueeze(1) * inv_freq
+        _ROPE_TABLES[key] = (torch.sin(angles).to(device).contiguous(), torch.cos(angles).to(device).contiguous())
+    return _ROPE_TABLES[key]
+
+
+class _Rope(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_dtype):
+        _need_cuda(x)
+        if x.dtype not in _DT:
+            x = x.float()
+        xc = x.contiguous()
+        B, S, D = xc.shape
+        sn, cs = _rope_tables(S, D, xc.device)
+        y = torch.empty(B, S, D, dtype=out_dtype, device=xc.device)
+        _lib.call("clipk_rope", xc.data_ptr(), _DT[xc.dtype], B * S, S, D, sn.data_ptr(), cs.data_ptr(), y.data_ptr(),
+                  _DT[out_dtype], 0, _stream())
+        ctx.cfg = (x.dtype, S, D)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xdt, S, D = ctx.cfg
+        if g.dtype not in _DT:
+            g = g.float()
+        gc = g.contiguous()
+        sn, cs = _rope_tables(S, D, gc.device)
+        dx = torch.empty(gc.shape, dtype=xdt if xdt in _DT else torch.float32, device=gc.device)
+        _lib.call("clipk_rope", gc.data_ptr(), _DT[gc.dtype], gc.shape[0] * S, S, D, sn.data_ptr(), cs.data_ptr(),
+                  dx.data_ptr(), _DT[dx.dtype], 1, _stream())
+        return dx.to(xdt), None
+
+
+def apply_rope(embeddings, out_dtype=None):
+    """Drop-in for `apply_rope` (pacl.py:147-181): embeddings [B, S, D] -> rotated [B, S, D] (same dtype unless
+    `out_dtype` is given; bf16 output feeds `VisualProjection` directly, as `open_clip_pacl_rope.forward` does)."""
+    assert embeddings.shape[-1] % 2 == 0, "Embedding dimension must be even for RoPE."
+    od = out_dtype or (embeddings.dtype if embeddings.dtype in _DT else torch.float32)
+    return _Rope.apply(embeddings, od)

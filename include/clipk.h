@@ -191,6 +191,11 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
  * consumes dY (bf16) and
  writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
  * clipk_linear_*: y = x W^T + b on bf16 rows, dx (nullable) bf16, dW / db fp32. */
+/* apply_rope (PACL/model/pacl.py:147-181) on token rows [B*S, D]: pairs (x[2j], x[2j+1]) rotated by
+ * the angle of (position = row % S, j), written de-interleaved (first halves, then second halves).  sin_t / cos_t: fp32
+ * [S, D/2] tables built by the caller exactly as the reference builds them.  inverse != 0: transposed rotation. */
+int clipk_rope(const void* x, int dtype_in, int64_t rows, int S, int D, const float* sin_t, const float* cos_t, void* y,
+               int dtype_out, int inverse, void* stream);
 int clipk_ln_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta, float eps,
                  void* xn, float* mean, float* rstd, void* stream);
 size_t clipk_ln_bwd_workspace_bytes(int64_t rows, int D);

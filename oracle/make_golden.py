@@ -275,8 +275,18 @@ def g7(pacl):
 def main_heads():
     assert refload.available(), "reference not found; run in the build container"
     torch.set_num_threads(8)
+    pacl = refload.load_pacl()
+    # G8: apply_rope (pacl.py:147-181) output and input gradient
+    xr = O.rn(25, 2, 50, 64).requires_grad_()
+    yr = pacl.apply_rope(xr)
+    (yr * O.rn(26, 2, 50, 64)).sum().backward()
+    xo = O.rn(25, 2, 50, 64).requires_grad_()
+    yo = O.apply_rope(xo)
+    (yo * O.rn(26, 2, 50, 64)).sum().backward()
+    _close(yo.detach(), yr.detach(), tol=1e-7, what="G8 rope y")
+    _close(xo.grad, xr.grad, tol=1e-7, what="G8 rope dx")
     G = dict(meta=dict(torch=torch.__version__, note="projection heads: outputs of the unmodified reference, CPU fp32"),
-             G7=g7(refload.load_pacl()))
+             G7=g7(pacl), G8=dict(y=yr.detach().clone(), dx=xr.grad.clone()))
     torch.save(G, os.path.join(OUT_DIR, "goldens_heads.pt"))
     print("G7 |y|", float(G["G7"]["y"].norm()), "|dx|", float(G["G7"]["dx"].norm()),
           "keys", sorted(G["G7"]["vis_sd"].keys()))

@@ -295,3 +295,13 @@ def mmvp_accounting(s1, s2, gt, pairs_per_cat=0, ncat=1):
         counts[cat][0] += int(ok == 2)
         counts[cat][1] += ok
     return counts, pred
+
+
+def apply_rope(embeddings):
+    """apply_rope, pacl.py:147-181 (restated line by line; pinned by golden G8 in goldens_heads.pt)."""
+    _, seq_length, dim = embeddings.shape
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+    angles = torch.arange(seq_length, dtype=torch.float).unsqueeze(1) * inv_freq
+    s, c = torch.sin(angles).unsqueeze(0), torch.cos(angles).unsqueeze(0)
+    x1, x2 = embeddings[..., 0::2], embeddings[..., 1::2]
+    return torch.cat([x1 * c - x2 * s, x1 * s + x2 * c], dim=-1)

@@ -97,3 +97,20 @@ def test_heads_feed_scorer_end_to_end():
     assert torch.isfinite(loss)
     for p in list(vis.parameters()) + list(txt.parameters()):
         assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0
+
+
+def test_rope_matches_reference_golden():
+    """apply_rope (pacl.py:147-181): fp32 path against the reference's own output and gradient (golden G8; the angle
+    tables are built with the reference's expressions, so only the two products per element can differ: <= 1e-6)."""
+    from clip_embeds_b200.heads import apply_rope
+    G8 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G8"]
+    x = O.rn(25, 2, 50, 64).cuda().requires_grad_()
+    y = apply_rope(x)
+    (y * O.rn(26, 2, 50, 64).cuda()).sum().backward()
+    assert (y.detach().cpu() - G8["y"]).abs().max().item() <= 1e-6
+    assert (x.grad.cpu() - G8["dx"]).abs().max().item() <= 1e-6
+    # bf16 in / bf16 out at the ViT-L/14-336 token shape against the oracle on the same bf16 inputs
+    xb = O.rn(27, 3, 576, 1024).to(torch.bfloat16)
+    yb = apply_rope(xb.cuda())
+    assert yb.dtype == torch.bfloat16
+    assert rel_l2(yb.float().cpu(), O.apply_rope(xb.float())) < 4e-3

@@ -107,3 +107,12 @@ def test_g7_projection_heads():
         assert rel_l2(sd[k].grad, g) < 1e-5, k
     for k, g in G["txt_grads"].items():
         assert rel_l2(sdt[k].grad, g) < 1e-5, k
+
+
+def test_g8_rope():
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G8"]
+    x = O.rn(25, 2, 50, 64).requires_grad_()
+    y = O.apply_rope(x)
+    (y * O.rn(26, 2, 50, 64)).sum().backward()
+    assert torch.allclose(y.detach(), G["y"], atol=1e-7) and torch.allclose(x.grad, G["dx"], atol=1e-7)
