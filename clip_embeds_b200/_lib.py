@@ -70,6 +70,8 @@ SIGNATURES = {
     "clipk_eval_whatsup": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "clipk_eval_mmvp": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "clipk_rope": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "clipk_retrieval_ranks": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "clipk_rank_stats": (c_int, [c_vp, c_int, c_vp, c_vp]),
 }
 
 _lib = None

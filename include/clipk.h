@@ -228,6 +228,15 @@ int clipk_eval_whatsup(const int* correct, const int* set_id, const int* rel_id,
 int clipk_eval_mmvp(const float* s_img1, const float* s_img2, const int* gt, int pairs, int pairs_per_cat, int ncat,
                     int* pred, int* counts, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Retrieval ranks fused into the logits GEMM (get_clip_metrics,
+ * open_clip/src/open_clip_train/train.py:360-377): X bf16 [M,D], Y bf16 [N,D]; rank_row[i] = #{j != i : <x_i,y_j> >
+ * <x_i,y_i>}, rank_col[j] = #{i != j : <x_i,y_j> > <x_j,y_j>} (0 = ground truth first); the logits are never written.
+ * clipk_rank_stats: (sum of ranks, #rank<1, #rank<5, #rank<10) as uint64[4] on the device. */
+int clipk_retrieval_ranks(const void* X, const void* Y, int M, int N, int D, float* diag_ws, int* rank_row,
+                          int* rank_col, void* stream);
+int clipk_rank_stats(const int* ranks, int n, unsigned long long* stats4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

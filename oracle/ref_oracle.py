@@ -305,3 +305,32 @@ def apply_rope(embeddings):
     s, c = torch.sin(angles).unsqueeze(0), torch.cos(angles).unsqueeze(0)
     x1, x2 = embeddings[..., 0::2], embeddings[..., 1::2]
     return torch.cat([x1 * c - x2 * s, x1 * s + x2 * c], dim=-1)
+
+
+# ----------------------------------------------------------------------------
+# Other InfoNCE users  -- SURVEY §8f rank 4
+# ----------------------------------------------------------------------------
+def clip_metrics(image_features, text_features, logit_scale):
+    """get_clip_metrics, open_clip/src/open_clip_train/train.py:360-377: descending argsort of the logits, position
+    of the ground truth, mean / median rank (+1), R@1/5/10.  Also returns the 0-based positions per direction."""
+    import numpy as np
+    logits_per_image = logit_scale * image_features @ text_features.t()
+    out, preds_all = {}, {}
+    gt = torch.arange(len(text_features)).view(-1, 1)
+    for name, logit in (("image_to_text", logits_per_image), ("text_to_image", logits_per_image.t())):
+        ranking = torch.argsort(logit, descending=True)
+        preds = torch.where(ranking == gt)[1].numpy()
+        preds_all[name] = preds
+        out[f"{name}_mean_rank"] = preds.mean() + 1
+        out[f"{name}_median_rank"] = np.floor(np.median(preds)) + 1
+        for k in (1, 5, 10):
+            out[f"{name}_R@{k}"] = np.mean(preds < k)
+    return out, preds_all
+
+
+def simple_contrastive_loss(x, y, temperature=0.02, target=None, reduction="mean"):
+    """SimpleContrastiveLoss.__call__, VLM2Vec/src/loss.py:11-19."""
+    if target is None:
+        tpq = y.size(0) // x.size(0)
+        target = torch.arange(0, x.size(0) * tpq, tpq, dtype=torch.long)
+    return F.cross_entropy(x @ y.t() / temperature, target, reduction=reduction)
