@@ -470,8 +470,48 @@ struct CeWorkspace {
   float2* part;
   float* pos;
   __nv_bfloat16* dL;
+  float* slabs;      // split-K slabs of dX: [nsplit][mc][D] fp32 (only when the dX GEMM is split)
 };
-static size_t ce_carve(CeWorkspace* w, void* base, int M, int N) {
+
+// dX = dL Y has only ceil(mc/256) * ceil(D/256) output tiles (48 for mc = 4096, D = 768) for 74 CTA pairs and a very
+// long K (= N): split K so that the tile count fills whole waves.  Returns the split count (1 = no split) and the
+// columns per split (a multiple of 64).
+struct DxSplit {
+  int nsplit;
+  int ksplit;
+};
+static DxSplit dx_split(int mc, int N, int D) {
+  DxSplit r{1, N};
+  if (mc <= eng::BM || N < 8192) return r;
+  const int tiles = ((mc + 255) / 256) * ((D + 255) / 256);
+  const int clusters = sm_count() / 2;
+  double best = (double)tiles / (((tiles + clusters - 1) / clusters) * (double)clusters);
+  for (int s = 2; s <= 8; ++s) {
+    if (N / s < 2048) break;
+    const int t = tiles * s;
+    const double eff = (double)t / (((t + clusters - 1) / clusters) * (double)clusters);
+    if (eff > best + 0.08) {       // a split costs a slab round trip: take it only for a clear gain
+      best = eff;
+      r.nsplit = s;
+    }
+  }
+  if (r.nsplit > 1) r.ksplit = (N / r.nsplit) / 64 * 64;      // rounded down: nsplit full splits + a short remainder
+  return r;
+}
+
+// dX[i] = (accumulate ? dX[i] : 0) + sum_s slabs[s][i]      (n % 4 == 0, fixed order)
+__global__ void ce_slab_reduce_kernel(const float4* __restrict__ slabs, int nslab, int64_t n4, int accumulate,
+                                      float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nslab; ++s) {
+    const float4 b = slabs[(int64_t)s * n4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+static size_t ce_carve(CeWorkspace* w, void* base, int M, int N, int D = 0) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void* p = base ? static_cast<char*>(base) + off : nullptr;
@@ -483,6 +523,11 @@ static size_t ce_carve(CeWorkspace* w, void* base, int M, int N) {
   w->part = static_cast<float2*>(take((size_t)M * tiles_n * sizeof(float2)));
   w->pos = static_cast<float*>(take((size_t)M * 4));
   w->dL = static_cast<__nv_bfloat16*>(take((size_t)mc * round_up_i(N, 64) * 2));
+  w->slabs = nullptr;
+  if (D > 0) {
+    const DxSplit sp = dx_split(mc, N, D);
+    if (sp.nsplit > 1) w->slabs = static_cast<float*>(take((size_t)sp.nsplit * mc * D * 4));
+  }
   return off;
 }
 
@@ -512,7 +557,8 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
                 int accX, float* dY, int accY, void* ws, size_t ws_bytes, cudaStream_t st) {
   CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_bwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
   CeWorkspace w{};
-  const size_t need = ce_carve(&w, ws, M, N);
+  size_t need = ce_carve(&w, ws, M, N, D);
+  if (ws_bytes < need) need = ce_carve(&w, ws, M, N);       // sized by the D-less query: run the dX GEMM unsplit
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "ce_feat_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int64_t ldd = round_up_i(N, 64);
   const int ksD[1] = {(D + 63) / 64};
@@ -534,7 +580,29 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       }
     }
     // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
-    if (dX != nullptr) {
+    const DxSplit sp = dx_split(mc, N, D);
+    if (dX != nullptr && sp.nsplit > 1 && w.slabs != nullptr && D % 4 == 0) {
+      // split-K: `nfull` splits of ksplit columns as the batches of one launch (slab s = batch s), the remaining
+      // columns in a second launch that accumulates into slab 0; then a fixed-order slab sum
+      const int nfull = N / sp.ksplit;
+      const int rem = N - nfull * sp.ksplit;
+      auto run = [&](int k0, int k, int batches, int accumulate) -> int {
+        OperandDesc a, b;
+        a.ptr = w.dL + k0; a.rows = mc; a.k = k; a.ld = ldd; a.batch = batches; a.batch_stride = k; a.bmul = 1;
+        b.ptr = Y + (int64_t)k0 * D; b.mn_major = true; b.rows = D; b.k = k; b.ld = D; b.batch = batches;
+        b.batch_stride = (int64_t)k * D; b.bmul = 1;
+        const int ks[1] = {(k + 63) / 64};
+        epi::Store<false>::Params ep{w.slabs, D, (int64_t)mc * D, mc, D, scale, accumulate};
+        return launch_gemm2<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, batches, ep, st);
+      };
+      CLIPK_TRY(run(0, sp.ksplit, nfull, 0));
+      if (rem > 0) CLIPK_TRY(run(nfull * sp.ksplit, rem, 1, 1));
+      const int64_t n4 = (int64_t)mc * D / 4;
+      ce_slab_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(w.slabs), nfull, n4, accX, reinterpret_cast<float4*>(dX + (int64_t)m0 * D));
+      clipk::count_launches(1);
+      CLIPK_CHECK_CUDA(cudaGetLastError());
+    } else if (dX != nullptr) {
       OperandDesc a, b;
       a.ptr = w.dL; a.rows = mc; a.k = N; a.ld = ldd;
       b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
@@ -646,6 +714,11 @@ int clipk_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
 size_t clipk_ce_feat_workspace_bytes(int M, int N) {
   clipk::CeWorkspace w{};
   return clipk::ce_carve(&w, nullptr, M, N);
+}
+
+size_t clipk_ce_feat_bwd_workspace_bytes(int M, int N, int D) {
+  clipk::CeWorkspace w{};
+  return clipk::ce_carve(&w, nullptr, M, N, D);
 }
 
 int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,

@@ -367,7 +367,8 @@ static WgradPlan wgrad_plan(int64_t rows, int out, int in) {
   if (want > max_split) want = (int)max_split;
   if (want < 1) want = 1;
   WgradPlan p;
-  p.ksplit = rup64((rows + want - 1) / want, 64);
+  p.ksplit = (rows / want) / 64 * 64;          // rounded down: `want` full splits + a short remainder
+  if (p.ksplit < 64) p.ksplit = 64;
   p.nsplit = (int)(rows / p.ksplit);
   p.rem = rows - (int64_t)p.nsplit * p.ksplit;
   if (p.nsplit == 0) {          // fewer tokens than one split: a single launch over everything

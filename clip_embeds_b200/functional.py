@@ -355,7 +355,7 @@ class _FeatRowCE(torch.autograd.Function):
         bi = float(bias) if bias is not None else 0.0
         if X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16:
             Xc, Yc = X.contiguous(), Y.contiguous()
-            nbytes = _lib.lib().clipk_ce_feat_workspace_bytes(M, N)
+            nbytes = _lib.lib().clipk_ce_feat_bwd_workspace_bytes(M, N, D)     # shared by forward and backward
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.call("clipk_ce_feat_fwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
                       row_lse.data_ptr(), row_loss.data_ptr(), ws.data_ptr(), nbytes, st)

@@ -140,6 +140,9 @@ int clipk_gemm_f32_split(const float* A, int64_t sam, int64_t sak, const float* 
  *        dX [M,D] / dY [N,D] fp32 (nullable; acc* != 0 accumulates into the buffer).
  */
 size_t clipk_ce_feat_workspace_bytes(int M, int N);
+/* backward workspace including the split-K slabs of the dX GEMM (a workspace sized by the query above still works:
+ * the dX GEMM then runs unsplit) */
+size_t clipk_ce_feat_bwd_workspace_bytes(int M, int N, int D);
 int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
                       const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
                       size_t ws_bytes, void* stream);
