@@ -53,18 +53,19 @@ pacl_paired_fwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
     for (int j = 0; j < 8; ++j) u[it][j] = 0.f;
 
   const T* Vb = V + (int64_t)(b / v_div) * P * D;
-  for (int p = warp; p < P; p += kPairedWarps) {
-    float v[NIT][8];
+  auto load_row = [&](int p, float (&v)[NIT][8]) {
     const T* row = Vb + (int64_t)p * D;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int d0 = it * 256 + lane * 8;
-      if (d0 < D) simt::load8<T>(row + d0, v[it]);
+      if (d0 < D && p < P) simt::load8<T>(row + d0, v[it]);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[it][j] = 0.f;
       }
     }
+  };
+  auto consume_row = [&](int p, const float (&v)[NIT][8]) {
     float r = 0.f, nsq = 0.f;
 #pragma unroll
     for (int it = 0; it < NIT; ++it)
@@ -84,6 +85,15 @@ pacl_paired_fwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
     for (int it = 0; it < NIT; ++it)
 #pragma unroll
       for (int j = 0; j < 8; ++j) u[it][j] = fmaf(a, v[it][j], u[it][j]);
+  };
+  // two rows per warp in flight: the occupancy is register-bound (2 CTAs / SM), so the bytes in flight per warp are
+  // what sets the achieved bandwidth
+  for (int p = warp; p < P; p += 2 * kPairedWarps) {
+    float v0[NIT][8], v1[NIT][8];
+    load_row(p, v0);
+    load_row(p + kPairedWarps, v1);
+    consume_row(p, v0);
+    if (p + kPairedWarps < P) consume_row(p + kPairedWarps, v1);
   }
   // ---- cross-warp reduction of the pooled vector
 #pragma unroll
