@@ -69,8 +69,8 @@ static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 // One warp per (b,t) row of S [rows, ld] (P valid columns).  Forward: min / max / threshold / row-normalise.
 //   stats[row] = (min, R = max - min + 1e-8, Zeps = sum + 1e-8, _), arg[row] = (argmin, argmax)  (first occurrence)
 __global__ void sparc_rows_fwd_kernel(const float* __restrict__ S, int64_t rows, int P, int ld, float sigma,
-                                      __nv_bfloat16* __restrict__ W, float4* __restrict__ stats,
-                                      int2* __restrict__ arg) {
+                                           __nv_bfloat16* __restrict__ W, float4* __restrict__ stats,
+                                           int2* __restrict__ arg) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -116,9 +116,11 @@ __global__ void sparc_rows_fwd_kernel(const float* __restrict__ S, int64_t rows,
 }
 
 // Backward through row-normalise / threshold / min-max:  dW [rows, ld] fp32 -> dS [rows, ld] bf16.
+//   c = sum_q dW_q W_q ;  dh_p = [h_p >= sigma] (dW_p - c) / zeps ;  dS_p = dh_p / R ;
+//   dmin = -sum dh/R + sum dh (S-mn)/R^2 ; dmax = -sum dh (S-mn)/R^2  (added at the arg positions)
 __global__ void sparc_rows_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dW, int64_t rows, int P,
-                                      int ld, float sigma, const float4* __restrict__ stats,
-                                      const int2* __restrict__ arg, __nv_bfloat16* __restrict__ dS) {
+                                           int ld, float sigma, const float4* __restrict__ stats,
+                                           const int2* __restrict__ arg, __nv_bfloat16* __restrict__ dS) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -127,7 +129,6 @@ __global__ void sparc_rows_bwd_kernel(const float* __restrict__ S, const float* 
   const float4 st = stats[row];
   const float mn = st.x, R = st.y, zeps = st.z;
   const int2 ag = arg[row];
-  // c = sum_q dW_q W_q
   float c = 0.f;
   for (int p = lane; p < P; p += 32) {
     float h = (s[p] - mn) / R;
@@ -135,7 +136,6 @@ __global__ void sparc_rows_bwd_kernel(const float* __restrict__ S, const float* 
     c = fmaf(dw[p], h / zeps, c);
   }
   c = ptx::warp_sum(c);
-  // dh_p = [h_p >= sigma] (dW_p - c) / zeps ;  dS_p = dh_p / R ;  dmin = -sum dh/R + sum dh (S-mn)/R^2 ; dmax = -sum dh (S-mn)/R^2
   float a1 = 0.f, a2 = 0.f;
   for (int p = lane; p < P; p += 32) {
     const float h = (s[p] - mn) / R;

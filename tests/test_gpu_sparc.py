@@ -48,6 +48,13 @@ def test_sparc_vitl_shape():
     assert e_g < 5e-3 and e_l < 1e-5 and dl < 5e-3 and rv < 4e-2 and rl < 4e-2
 
 
+@pytest.mark.parametrize("T,P,D", [(33, 625, 256), (16, 50, 128), (40, 700, 128)])
+def test_sparc_ragged_shapes(T, P, D):
+    """Patch counts that are not multiples of 32 / 64: ViT-B/16 at 400 px (625), a short row (50), a long one (700)."""
+    e_g, e_l, dl, rv, rl = _run(3, T, P, D, 90 + T, [T - 1, T // 2, 3])
+    assert e_g < 5e-3 and e_l < 1e-5 and dl < 5e-3 and rv < 4e-2 and rl < 4e-2
+
+
 def test_sparc_golden_fp32_inputs(goldens):
     """Reference golden G2 (fp32 reference, fp32 inputs): input rounding to bf16 is part of the error."""
     from clip_embeds_b200.losses import SparcLoss
