@@ -318,11 +318,52 @@ class _MatmulNT(torch.autograd.Function):
         return dX.to(xdt), dY.to(ydt), None
 
 
+class _MatmulNTBf16(torch.autograd.Function):
+    """L (fp32) = alpha * X @ Y.T for bf16 features on the tcgen05 engine; backward: dL is rounded to bf16 and feeds
+    two engine GEMMs (fp32 gradients)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, alpha):
+        _need_cuda(X, Y)
+        Xc, Yc = X.contiguous(), Y.contiguous()
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        L = _f32(M, N, device=Xc.device)
+        _lib.call("clipk_gemm_bf16", Xc.data_ptr(), 0, D, 0, Yc.data_ptr(), 0, D, 0, L.data_ptr(), N, 0, 1, M, N, D, 1,
+                  float(alpha), 0, _stream())
+        ctx.save_for_backward(Xc, Yc)
+        ctx.alpha = float(alpha)
+        return L
+
+    @staticmethod
+    def backward(ctx, dL):
+        Xc, Yc = ctx.saved_tensors
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        g = dL.to(torch.bfloat16).contiguous()
+        dX, dY = _f32(M, D, device=Xc.device), _f32(N, D, device=Xc.device)
+        st = _stream()
+        # dX = alpha * dL Y      (A = dL [M,N] K-major, B = Y as a [K = N][D] MN-major operand)
+        _lib.call("clipk_gemm_bf16", g.data_ptr(), 0, N, 0, Yc.data_ptr(), 1, D, 0, dX.data_ptr(), D, 0, 1, M, D, N, 1,
+                  ctx.alpha, 0, st)
+        # dY = alpha * dL^T X    (A = dL read MN-major: rows = n, k = m; B = X MN-major)
+        _lib.call("clipk_gemm_bf16", g.data_ptr(), 1, N, 0, Xc.data_ptr(), 1, D, 0, dY.data_ptr(), D, 0, 1, N, D, M, 1,
+                  ctx.alpha, 0, st)
+        return dX.to(Xc.dtype), dY.to(Yc.dtype), None
+
+
+_SYMMETRIC_DENSE_MAX = 8192        # [B,B] fp32 logits up to 256 MB; larger batches stream (logits never written)
+
+
 def symmetric_infonce(X, Y, scale):
     """1/2 [CE(scale X Y^T, I) + CE(scale Y X^T, I)] (pacl.py:498-514).  fp32 features: ONE logits GEMM (the text-side
     logits are its transpose), row + column CE on the fp32 matrix, two gradient GEMMs; bf16 features: the
     tensor-core feature CE (logits never written)."""
     if X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16:
+        if X.shape[0] == Y.shape[0] and X.shape[0] <= _SYMMETRIC_DENSE_MAX and X.shape[1] % 8 == 0:
+            # small symmetric batch (PACL ClipLoss): one logits GEMM instead of two forward + two recompute GEMMs,
+            # row and column CE on the fp32 matrix, two gradient GEMMs -- 3 tensor-core launches instead of 8
+            return score_infonce(_MatmulNTBf16.apply(X, Y, float(scale)), 0, None)
         return (feat_row_ce(X, Y, scale) + feat_row_ce(Y, X, scale)) / 2
     if X.shape[0] != Y.shape[0]:
         raise ValueError(f"symmetric InfoNCE needs as many rows in X as in Y ({X.shape[0]} vs {Y.shape[0]})")

@@ -54,9 +54,11 @@ def test_openclip_hardneg_bf16_engine(shape):
     assert abs(scale.grad.item() - so.grad.item()) < 2e-2 * max(1e-3, abs(so.grad.item())) + 1e-5
 
 
-def test_pacl_cliploss_bf16():
+@pytest.mark.parametrize("B", [512, 2048])
+def test_pacl_cliploss_bf16(B):
+    """bf16 ClipLoss (small symmetric batch: one tensor-core logits GEMM, fp32 row + column CE, two gradient GEMMs)."""
     from clip_embeds_b200.losses import ClipLoss
-    B, D = 512, 768
+    D = 768
     ib = O.l2n(O.rn(61, B, D)).to(torch.bfloat16)
     tb = O.l2n(O.rn(62, B, D)).to(torch.bfloat16)
     io = ib.float().requires_grad_()
