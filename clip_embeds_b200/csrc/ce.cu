@@ -495,7 +495,7 @@ static DxSplit dx_split(int mc, int N, int D) {
       r.nsplit = s;
     }
   }
-  if (r.nsplit > 1) r.ksplit = (N / r.nsplit) / 64 * 64;      // rounded down: nsplit full splits + a short remainder
+  if (r.nsplit > 1) r.ksplit = ((N + r.nsplit - 1) / r.nsplit + 63) / 64 * 64;    // nsplit splits cover N; tail zero-filled
   return r;
 }
 
@@ -582,21 +582,18 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
     // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
     const DxSplit sp = dx_split(mc, N, D);
     if (dX != nullptr && sp.nsplit > 1 && w.slabs != nullptr && D % 4 == 0) {
-      // split-K: `nfull` splits of ksplit columns as the batches of one launch (slab s = batch s), the remaining
-      // columns in a second launch that accumulates into slab 0; then a fixed-order slab sum
-      const int nfull = N / sp.ksplit;
-      const int rem = N - nfull * sp.ksplit;
-      auto run = [&](int k0, int k, int batches, int accumulate) -> int {
+      // split-K: the splits are the batches of ONE launch (slab s = batch s); batch s starts at column s * ksplit of
+      // the single long reduction dim, the operand maps keep the true extent N, so the last split's tail is
+      // zero-filled by TMA; then a fixed-order slab sum
+      const int nfull = (N + sp.ksplit - 1) / sp.ksplit;
+      {
         OperandDesc a, b;
-        a.ptr = w.dL + k0; a.rows = mc; a.k = k; a.ld = ldd; a.batch = batches; a.batch_stride = k; a.bmul = 1;
-        b.ptr = Y + (int64_t)k0 * D; b.mn_major = true; b.rows = D; b.k = k; b.ld = D; b.batch = batches;
-        b.batch_stride = (int64_t)k * D; b.bmul = 1;
-        const int ks[1] = {(k + 63) / 64};
-        epi::Store<false>::Params ep{w.slabs, D, (int64_t)mc * D, mc, D, scale, accumulate};
-        return launch_gemm2<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, batches, ep, st);
-      };
-      CLIPK_TRY(run(0, sp.ksplit, nfull, 0));
-      if (rem > 0) CLIPK_TRY(run(nfull * sp.ksplit, rem, 1, 1));
+        a.ptr = w.dL; a.rows = mc; a.k = N; a.ld = ldd; a.k_batch_offset = sp.ksplit;
+        b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
+        const int ks[1] = {(sp.ksplit + 63) / 64};
+        epi::Store<false>::Params ep{w.slabs, D, (int64_t)mc * D, mc, D, scale, 0};
+        CLIPK_TRY((launch_gemm2<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, nfull, ep, st)));
+      }
       const int64_t n4 = (int64_t)mc * D / 4;
       ce_slab_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
           reinterpret_cast<const float4*>(w.slabs), nfull, n4, accX, reinterpret_cast<float4*>(dX + (int64_t)m0 * D));

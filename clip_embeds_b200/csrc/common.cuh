@@ -80,6 +80,8 @@ struct OperandDesc {
   int sub_per_batch = 0;     // split-K: sub = b * sub_per_batch + (kstep / ksub)
   int sub_total = 0;         // >0: uneven split, batch b covers sub-batches [b*spb, min((b+1)*spb, sub_total))
   int reverse = 0;           // (read from operand A of pair 0) walk batches downwards
+  int64_t k_batch_offset = 0;  // (operand A of each pair; CTA-pair engine) batch b covers k in [b * off, b * off + ksteps * 64)
+                               // of ONE long reduction dim: describe the operands with their true k extent, batch = 1
 };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -175,6 +177,7 @@ int launch_gemm2(const OperandDesc* a, const OperandDesc* b, int num_pairs, cons
     pb.b_bmul[q] = b[q].bmul; pb.b_smul[q] = b[q].smul;
     pb.sub_per_batch[q] = a[q].sub_per_batch;
     pb.sub_total[q] = a[q].sub_total;
+    pb.k_boff[q] = (int)a[q].k_batch_offset;
     if (!A_MN) {
       CLIPK_TRY(make_tmap_bf16(&maps.a[q], a[q].ptr, a[q].k, a[q].rows, a[q].batch, a[q].ld * 2, a[q].batch_stride * 2, eng2::BM));
     } else {

@@ -186,7 +186,7 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
           const int nks = ksteps_of(pb, q, tc.b);
           for (int ks = 0; ks < nks; ++ks) {
             const int subl = ks / pb.ksub[q];
-            const int k0 = (ks - subl * pb.ksub[q]) * BK;
+            const int k0 = (ks - subl * pb.ksub[q]) * BK + tc.b * pb.k_boff[q];
             const int sub = subl + tc.b * pb.sub_per_batch[q];
             const int ab = tc.b * pb.a_bmul[q] + sub * pb.a_smul[q];
             const int bb = tc.b * pb.b_bmul[q] + sub * pb.b_smul[q];

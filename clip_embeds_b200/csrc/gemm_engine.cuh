@@ -114,6 +114,8 @@ struct Problem {
   int sub_total[2];          // >0: batch b only covers sub-batches [b*spb, min((b+1)*spb, sub_total)) (uneven split)
   int reverse;               // walk the batch index downwards: consecutive launches alternate direction so that a
                              // launch first touches what the previous one wrote last (still L2-resident)
+  int k_boff[2];             // CTA-pair engine only: batch b starts at k = b * k_boff (plain split-K of one long K:
+                             // the maps keep the TRUE k extent, so the last split's tail is zero-filled by TMA)
 };
 
 template <int BN, bool DUAL = false, bool TMA_OUT = false>

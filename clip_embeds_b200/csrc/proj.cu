@@ -355,9 +355,8 @@ static int colsum_launch(const __nv_bfloat16* G, const T* X, const float* mean, 
 // dW [out, in] = G^T X over `rows` tokens (G bf16 [rows, out], X bf16 [rows, in]); split-K over token blocks into
 // fp32 slabs, summed in a fixed order.
 struct WgradPlan {
-  int nsplit;        // full splits (batches of the first launch)
-  int64_t ksplit;    // tokens per split (multiple of 64)
-  int64_t rem;       // tokens left for the remainder launch (accumulated into slab 0)
+  int nsplit;        // splits = batches of the one launch
+  int64_t ksplit;    // tokens per split (multiple of 64); the last split's tail is zero-filled by TMA
 };
 static WgradPlan wgrad_plan(int64_t rows, int out, int in) {
   const int tiles = ((out + 255) / 256) * ((in + 255) / 256);
@@ -367,15 +366,8 @@ static WgradPlan wgrad_plan(int64_t rows, int out, int in) {
   if (want > max_split) want = (int)max_split;
   if (want < 1) want = 1;
   WgradPlan p;
-  p.ksplit = (rows / want) / 64 * 64;          // rounded down: `want` full splits + a short remainder
-  if (p.ksplit < 64) p.ksplit = 64;
-  p.nsplit = (int)(rows / p.ksplit);
-  p.rem = rows - (int64_t)p.nsplit * p.ksplit;
-  if (p.nsplit == 0) {          // fewer tokens than one split: a single launch over everything
-    p.nsplit = 1;
-    p.ksplit = rows;
-    p.rem = 0;
-  }
+  p.ksplit = rup64((rows + want - 1) / want, 64);
+  p.nsplit = (int)((rows + p.ksplit - 1) / p.ksplit);
   return p;
 }
 static size_t wgrad_ws_bytes(int64_t rows, int out, int in) {
@@ -386,18 +378,17 @@ static int wgrad_splitk(const __nv_bfloat16* G, int out, const __nv_bfloat16* X,
                         float* dW, cudaStream_t st) {
   const WgradPlan pl = wgrad_plan(rows, out, in);
   CLIPK_REQUIRE(out % 8 == 0 && in % 8 == 0, "wgrad: feature dims must be multiples of 8 (out=%d in=%d)", out, in);
-  auto run = [&](const __nv_bfloat16* g, const __nv_bfloat16* x, int64_t k, int batches, int accumulate) -> int {
+  {
+    // one launch: batch s covers tokens [s * ksplit, (s + 1) * ksplit) of the single long K (= tokens); the maps keep
+    // the true extent `rows`
     OperandDesc a, b;
-    a.ptr = g; a.mn_major = true; a.rows = out; a.k = k; a.ld = out; a.batch = batches; a.batch_stride = k * out; a.bmul = 1;
-    b.ptr = x; b.mn_major = true; b.rows = in; b.k = k; b.ld = in; b.batch = batches; b.batch_stride = k * in; b.bmul = 1;
-    const int ks[1] = {(int)((k + 63) / 64)};
-    epi::Store<false>::Params ep{slabs, in, (int64_t)out * in, out, in, 1.f, accumulate};
-    if (in > 128) return launch_gemm2<256, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, out, in, batches, ep, st);
-    return launch_gemm2<128, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, out, in, batches, ep, st);
-  };
-  CLIPK_TRY(run(G, X, pl.ksplit, pl.nsplit, 0));
-  if (pl.rem > 0)
-    CLIPK_TRY(run(G + (int64_t)pl.nsplit * pl.ksplit * out, X + (int64_t)pl.nsplit * pl.ksplit * in, pl.rem, 1, 1));
+    a.ptr = G; a.mn_major = true; a.rows = out; a.k = rows; a.ld = out; a.k_batch_offset = pl.ksplit;
+    b.ptr = X; b.mn_major = true; b.rows = in; b.k = rows; b.ld = in;
+    const int ks[1] = {(int)(pl.ksplit / 64)};
+    epi::Store<false>::Params ep{slabs, in, (int64_t)out * in, out, in, 1.f, 0};
+    if (in > 128) CLIPK_TRY((launch_gemm2<256, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, out, in, pl.nsplit, ep, st)));
+    else CLIPK_TRY((launch_gemm2<128, true, true, epi::Store<false>>(&a, &b, 1, ks, ks, out, in, pl.nsplit, ep, st)));
+  }
   const int64_t n4 = (int64_t)out * in / 4;
   slab_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(slabs), pl.nsplit, n4,
                                                                    reinterpret_cast<float4*>(dW));
