@@ -293,7 +293,7 @@ namespace epi {
 // per-(row, n-tile) online log-sum-exp partial of logits = scale * acc + bias; captures the label logit.
 struct LsePart {
   struct Params {
-    float2* part;            // [M][tiles_n] (max, sumexp); tiles_n counts HALF tiles (two epilogue warps per row)
+    float2* part;            // [tiles_n][M] (max, sumexp); tiles_n counts HALF tiles (two epilogue warps per row)
     float* pos;              // [M] logit at the label column (written by the tile that owns it)
     const int64_t* labels;   // nullable
     int64_t label_offset;
@@ -334,7 +334,7 @@ struct LsePart {
     }
   }
   __device__ void tile_end(int, int m, int, int tn, int half) {
-    if (m < p.M) p.part[(int64_t)m * p.tiles_n + 2 * tn + half] = make_float2(mx, sm);
+    if (m < p.M) p.part[(int64_t)(2 * tn + half) * p.M + m] = make_float2(mx, sm);     // [tiles_n][M]: lanes = rows, coalesced
   }
 };
 
@@ -421,16 +421,17 @@ struct DlOutTma {
 
 namespace clipk {
 
+// partials are laid out [tiles_n][M] (written coalesced by the epilogue warps, lanes = rows): one thread per row
 __global__ void lse_merge_kernel(const float2* __restrict__ part, const float* __restrict__ pos, int M, int tiles_n,
                                  const int64_t* __restrict__ labels, int64_t label_offset, int N,
                                  float* __restrict__ row_lse, float* __restrict__ row_loss) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float mx = -INFINITY;
-  for (int t = 0; t < tiles_n; ++t) mx = fmaxf(mx, part[(int64_t)m * tiles_n + t].x);
+  for (int t = 0; t < tiles_n; ++t) mx = fmaxf(mx, part[(int64_t)t * M + m].x);
   float sm = 0.f;
   for (int t = 0; t < tiles_n; ++t) {
-    const float2 q = part[(int64_t)m * tiles_n + t];
+    const float2 q = part[(int64_t)t * M + m];
     if (q.x > -INFINITY) sm += q.y * expf(q.x - mx);
   }
   const float lse = mx + logf(sm);
@@ -546,7 +547,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
   epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
   CLIPK_TRY((ce_launch<256, false, false, epi::LsePart>(ce_engine(M), &a, &b, ks, M, N, ep, st)));
-  lse_merge_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
+  lse_merge_kernel<<<(M + 127) / 128, 128, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
   clipk::count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
