@@ -467,6 +467,19 @@ static int ce_launch(int engine, const OperandDesc* a, const OperandDesc* b, con
   return launch_gemm<BN, A_MN, B_MN, Epi>(a, b, 1, ks, ks, M, N, 1, ep, st);
 }
 
+// bf16 output variant (gradients wanted in bf16: no fp32 round trip + cast pass)
+__global__ void ce_slab_reduce_bf16_kernel(const float4* __restrict__ slabs, int nslab, int64_t n4,
+                                           uint2* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nslab; ++s) {
+    const float4 b = slabs[(int64_t)s * n4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = make_uint2(ptx::pack_bf16x2(a.x, a.y), ptx::pack_bf16x2(a.z, a.w));
+}
+
 struct CeWorkspace {
   float2* part;
   float* pos;
@@ -554,9 +567,16 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
 }
 
 int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
-                const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
-                int accX, float* dY, int accY, void* ws, size_t ws_bytes, cudaStream_t st) {
+                const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, void* dXv,
+                int accX, void* dYv, int accY, int grads_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
   CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_bwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
+  // bf16 gradients: written straight from the GEMM epilogues (TMA stores) / the slab sum; needs a single row chunk
+  // (dY is not accumulated across chunks) and the CTA-pair engine
+  CLIPK_REQUIRE(!grads_bf16 || (accX == 0 && accY == 0 && M <= kCeChunkRows && M > eng::BM && N > eng::BM),
+                "ce_feat_bwd: bf16 gradients need %d < M <= %d, N > %d and no accumulation (M=%d N=%d)", eng::BM,
+                kCeChunkRows, eng::BM, M, N);
+  float* dX = static_cast<float*>(dXv);
+  float* dY = static_cast<float*>(dYv);
   CeWorkspace w{};
   size_t need = ce_carve(&w, ws, M, N, D);
   if (ws_bytes < need) need = ce_carve(&w, ws, M, N);       // sized by the D-less query: run the dX GEMM unsplit
@@ -596,8 +616,12 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
         CLIPK_TRY((launch_gemm2<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, nfull, ep, st)));
       }
       const int64_t n4 = (int64_t)mc * D / 4;
-      ce_slab_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
-          reinterpret_cast<const float4*>(w.slabs), nfull, n4, accX, reinterpret_cast<float4*>(dX + (int64_t)m0 * D));
+      if (grads_bf16)
+        ce_slab_reduce_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(w.slabs), nfull, n4, reinterpret_cast<uint2*>(dXv));
+      else
+        ce_slab_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(w.slabs), nfull, n4, accX, reinterpret_cast<float4*>(dX + (int64_t)m0 * D));
       clipk::count_launches(1);
       CLIPK_CHECK_CUDA(cudaGetLastError());
     } else if (dX != nullptr) {
@@ -605,8 +629,13 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       a.ptr = w.dL; a.rows = mc; a.k = N; a.ld = ldd;
       b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
       const int ks[1] = {(N + 63) / 64};
-      epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX};
-      CLIPK_TRY((ce_launch<256, false, true, epi::Store<false>>(ce_engine(mc), &a, &b, ks, mc, D, ep, st)));
+      if (grads_bf16) {
+        epi::StoreTma::Params ep{{dXv, D, (int64_t)mc * D, mc, D, 1}, scale};
+        CLIPK_TRY((launch_gemm2<256, false, true, epi::StoreTma>(&a, &b, 1, ks, ks, mc, D, 1, ep, st)));
+      } else {
+        epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX};
+        CLIPK_TRY((ce_launch<256, false, true, epi::Store<false>>(ce_engine(mc), &a, &b, ks, mc, D, ep, st)));
+      }
     }
     // dY (+)= scale * dL^T X[m0:m0+mc]        (A = dL MN-major (rows = n), B = X MN-major)
     if (dY != nullptr) {
@@ -614,8 +643,13 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       a.ptr = w.dL; a.mn_major = true; a.rows = N; a.k = mc; a.ld = ldd;
       b.ptr = X + (int64_t)m0 * D; b.mn_major = true; b.rows = D; b.k = mc; b.ld = D;
       const int ks[1] = {(mc + 63) / 64};
-      epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0};
-      CLIPK_TRY((ce_launch<256, true, true, epi::Store<false>>(ce_engine(N), &a, &b, ks, N, D, ep, st)));
+      if (grads_bf16) {
+        epi::StoreTma::Params ep{{dYv, D, (int64_t)N * D, N, D, 1}, scale};
+        CLIPK_TRY((launch_gemm2<256, true, true, epi::StoreTma>(&a, &b, 1, ks, ks, N, D, 1, ep, st)));
+      } else {
+        epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0};
+        CLIPK_TRY((ce_launch<256, true, true, epi::Store<false>>(ce_engine(N), &a, &b, ks, N, D, ep, st)));
+      }
     }
   }
   return 0;
@@ -733,7 +767,16 @@ int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float s
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
-                            bias, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, workspace, ws_bytes,
+                            bias, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, 0, workspace, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                           const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w,
+                           void* dX, void* dY, void* workspace, size_t ws_bytes, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
+                            bias, labels, label_offset, row_lse, row_w, dX, 0, dY, 0, 1, workspace, ws_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 }

@@ -428,6 +428,15 @@ class _FeatRowCE(torch.autograd.Function):
         st = _stream()
         lab_ptr = labels.data_ptr() if has_labels else 0
         row_w = (valid.float() * g_sum.float()).contiguous()
+        if (Xc.dtype == torch.bfloat16 and xdt == torch.bfloat16 and ydt == torch.bfloat16 and 128 < M <= 4096 and N > 128
+                and not ctx.scale_needs_grad):
+            # bf16 gradients straight from the GEMM epilogues (no fp32 round trip + cast pass)
+            dXb = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+            dYb = torch.empty(N, D, dtype=torch.bfloat16, device=dev)
+            ws = ctx.ws
+            _lib.call("clipk_ce_feat_bwd_bf16", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
+                      row_lse.data_ptr(), row_w.data_ptr(), dXb.data_ptr(), dYb.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            return dXb, dYb, None, None, None, None
         dX, dY = _f32(M, D, device=dev), _f32(N, D, device=dev)
         if Xc.dtype == torch.bfloat16:
             ws = ctx.ws

@@ -150,6 +150,12 @@ int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float s
                       const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream);
 
+/* The same backward with bf16 gradients written straight from the GEMM epilogues (dX, dY bf16, both required, no
+ * accumulation); supported for 128 < M <= 4096 and N > 128 (CLIPK_ERR_INVALID otherwise: use the fp32 entry). */
+int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                           const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w,
+                           void* dX, void* dY, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * SPARC token-to-patch alignment (sparc.forward, PACL/model/pacl.py:453-478):
  *   S = L V^T (raw), min-max over patches, threshold sigma, row-normalise, G = W V; outputs l_hat = n(L),
