@@ -83,3 +83,35 @@ def test_sparc_scoring():
         ref = O.sparc_scoring(Vb.float(), Lb.float(), mask, 1.0 / P, local=local)
         out = SparcHead(1.0 / P).scoring(Vb.cuda(), Lb.cuda(), mask.cuda(), local=local)
         assert (out.cpu() - ref).abs().max().item() < 5e-3
+
+
+def test_sparc_step_cuda_graph_replay_is_bit_identical():
+    """The whole SPARC forward + backward (alignment, SparcLoss, every libclipk launch incl. programmatic dependent
+    launches and host-encoded tensor maps) captured once with `GraphedStep` and replayed: same loss and gradients, bit
+    for bit, as the eager step -- the library never synchronises or allocates, so a step is capturable."""
+    from clip_embeds_b200.graphs import GraphedStep
+    from clip_embeds_b200.losses import SparcLoss
+    from clip_embeds_b200.models import SparcHead
+    B, T, P, D = 8, 77, 196, 256
+    V = O.rn(95, B, P, D).to(torch.bfloat16).cuda().requires_grad_()
+    L = O.rn(96, B, T, D).to(torch.bfloat16).cuda().requires_grad_()
+    mask = (torch.arange(T).expand(B, -1) <= torch.tensor([5, 76, 20, 9, 50, 30, 11, 70]).unsqueeze(1)).float().cuda()
+    head, sl = SparcHead(1.0 / P), SparcLoss(0.1)
+
+    def step():
+        if V.grad is not None:
+            V.grad.zero_()
+            L.grad.zero_()
+        v2, lh, gh, m2 = head(V, L, mask)
+        loss = sl(v2, lh, gh, m2)
+        loss.backward()
+        return loss
+
+    ref = step().item()
+    gV, gL = V.grad.clone(), L.grad.clone()
+    gs = GraphedStep(step)
+    for _ in range(2):
+        gs.replay()
+    torch.cuda.synchronize()
+    assert gs.loss.item() == ref
+    assert torch.equal(V.grad, gV) and torch.equal(L.grad, gL)
