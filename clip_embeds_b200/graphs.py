@@ -12,8 +12,10 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, warmup=3):
-        """`step_fn()` runs one forward + backward on static tensors and returns the loss tensor."""
+    def __init__(self, step_fn, warmup=3, capture_error_mode="global"):
+        """`step_fn()` runs one forward + backward on static tensors and returns the loss tensor.
+        `capture_error_mode="thread_local"` tolerates CUDA calls of other threads during capture (the NCCL watchdog
+        of `torch.distributed` polls events) -- needed when the step contains collectives."""
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -22,7 +24,7 @@ class GraphedStep:
                 step_fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = step_fn()
 
     def replay(self):
