@@ -63,6 +63,23 @@ def _patch_cpu_kernels():
     Fk._k_ce_payload, Fk._k_ce_merge = k_payload, k_merge
     Fk._need_cuda = lambda *a: None
     Fk.pacl_scores = lambda V, T, c=1.0, activation="sigmoid", group=None: O.pacl_allpairs_scores(V, T, c, activation)
+    # SPARC host logic: CPU stand-ins for the row kernels and the local term
+    Fk.normalize_rows = O.l2n
+    Fk.mean_dim1 = lambda X: X.float().mean(dim=1)
+    Fk.pooled_patch_mean = lambda V: V.float().mean(dim=1)
+
+    def local_loss(g_hat, l_hat, mask, scale, mask_sum=None):
+        # 1/2 [ masked_pairwise(g, l) + masked_pairwise(l, g) ] with the (possibly GLOBAL) mask count as denominator
+        m = mask.reshape(-1)
+        num = 0.0
+        for a, b in ((g_hat, l_hat), (l_hat, g_hat)):
+            B, T, _ = a.shape
+            logits = torch.einsum("bmd,bnd->bmn", a, b) * scale + ((1.0 - mask) * (-1e8)).unsqueeze(1)
+            tgt = torch.eye(T).unsqueeze(0).expand(B, -1, -1).reshape(B * T, -1)
+            num = num + (F.cross_entropy(logits.reshape(B * T, -1), tgt, reduction="none") * m).sum()
+        return num * 0.5 / (m.sum() if mask_sum is None else mask_sum)
+
+    Fk.sparc_local_loss = local_loss
 
 
 def _worker(rank, world, port, case, q):
@@ -98,6 +115,17 @@ def _worker(rank, world, port, case, q):
             loss = losses.PaclAllPairsLoss(0.1, group=dist.group.WORLD)(Vl, Tl)
             loss.backward()
             q.put((rank, loss.item(), Vl.grad.tolist(), Tl.grad.tolist()))
+        elif case == "sparc":
+            B, T_, P, D = 6, 9, 12, 16
+            V, L = O.rn(93, B, P, D), O.rn(94, B, T_, D)
+            mask = (torch.arange(T_).expand(B, -1) <= torch.tensor([2, 8, 5, 0, 7, 3]).unsqueeze(1)).float()
+            b = B // world
+            sl = slice(rank * b, (rank + 1) * b)
+            Vl, Ll = V[sl].clone().requires_grad_(), L[sl].clone().requires_grad_()
+            v, lh, gh, m = O.sparc_forward(Vl, Ll, mask[sl], 1.0 / P)      # the alignment itself is per sample
+            loss = losses.SparcLoss(0.1, group=dist.group.WORLD)(v, lh, gh, m)
+            loss.backward()
+            q.put((rank, loss.item(), Vl.grad.tolist(), Ll.grad.tolist()))
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -135,3 +163,20 @@ def test_allpairs_sharded_two_ranks():
         assert abs(res[r][1] - lo.item()) < 1e-5                      # every rank returns the global loss
         assert torch.allclose(torch.tensor(res[r][2]), V.grad[r * 3:(r + 1) * 3], atol=1e-6)
         assert torch.allclose(torch.tensor(res[r][3]), T.grad[r * 3:(r + 1) * 3], atol=1e-6)
+
+
+def test_sparc_sharded_two_ranks():
+    """SparcLoss with `group` (sample-sharded): gathered global term, local term over the GLOBAL mask count, scalar
+    all-reduce -- equals the single-process loss on the whole batch (the reference's DataParallel semantics,
+    train_sparc.py:92-94), and every rank gets the gradient of the global loss for its samples."""
+    res = _spawn("sparc")
+    B, T_, P, D = 6, 9, 12, 16
+    V, L = O.rn(93, B, P, D).requires_grad_(), O.rn(94, B, T_, D).requires_grad_()
+    mask = (torch.arange(T_).expand(B, -1) <= torch.tensor([2, 8, 5, 0, 7, 3]).unsqueeze(1)).float()
+    v, lh, gh, m = O.sparc_forward(V, L, mask, 1.0 / P)
+    lo = O.sparc_loss(v, lh, gh, m, 0.1)
+    lo.backward()
+    for r in range(2):
+        assert abs(res[r][1] - lo.item()) < 1e-5
+        assert torch.allclose(torch.tensor(res[r][2]), V.grad[r * 3:(r + 1) * 3], atol=1e-5)
+        assert torch.allclose(torch.tensor(res[r][3]), L.grad[r * 3:(r + 1) * 3], atol=1e-5)
