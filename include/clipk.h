@@ -197,8 +197,7 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
  *   clipk_ln_bwd : dgamma, dbeta [D] from dxn (bf16); dx (nullable; dtype of x) = gradient wrt the LayerNorm input
  * Patch_Projection: y = W1 xn + b1 + W3 gelu(W2 xn + b2) + b3 (erf GELU).  Weights bf16 [out, in], biases fp32,
  * b13 = b1 + b3.  fwd writes Gp = gelu'(z), H = gelu(z) (saved for the backward) and Y (all bf16 [R, Dout]); bwd
- * consumes dY (bf16) and
- writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
+ * consumes dY (bf16) and writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
  * clipk_linear_*: y = x W^T + b on bf16 rows, dx (nullable) bf16, dW / db fp32. */
 /* apply_rope (PACL/model/pacl.py:147-181) on token rows [B*S, D]: pairs (x[2j], x[2j+1]) rotated by
  * the angle of (position = row % S, j), written de-interleaved (first halves, then second halves).  sin_t / cos_t: fp32
