@@ -285,8 +285,31 @@ def main_heads():
     (yo * O.rn(26, 2, 50, 64)).sum().backward()
     _close(yo.detach(), yr.detach(), tol=1e-7, what="G8 rope y")
     _close(xo.grad, xr.grad, tol=1e-7, what="G8 rope dx")
+    # G9: get_clip_metrics (open_clip_train/train.py:360-377), the reference's own function on seeded features
+    gcm = refload.load_get_clip_metrics()
+    gq = torch.Generator().manual_seed(77)
+    base = torch.randn(200, 32, generator=gq)
+    gi = O.l2n(base + 2.0 * torch.randn(200, 32, generator=gq))
+    gt_ = O.l2n(base + 2.0 * torch.randn(200, 32, generator=gq))
+    ref_m = {k: float(v) for k, v in gcm(gi, gt_, torch.tensor(100.0)).items()}
+    our_m, _ = O.clip_metrics(gi, gt_, 100.0)
+    for k, v in ref_m.items():
+        _close(float(our_m[k]), v, tol=1e-9, what=f"G9 {k}")
+    # G10: VLM2Vec SimpleContrastiveLoss (src/loss.py:7-19), value and gradients
+    vl = refload.load_vlm2vec_loss()
+    xq = O.l2n(O.rn(28, 6, 16)).requires_grad_()
+    yq = O.l2n(O.rn(29, 18, 16)).requires_grad_()
+    lq = vl.SimpleContrastiveLoss(0.02)(xq, yq)
+    lq.backward()
+    xo2, yo2 = O.l2n(O.rn(28, 6, 16)).requires_grad_(), O.l2n(O.rn(29, 18, 16)).requires_grad_()
+    lo2 = O.simple_contrastive_loss(xo2, yo2, 0.02)
+    lo2.backward()
+    _close(lo2.detach(), lq.detach(), what="G10 loss")
+    _close(xo2.grad, xq.grad, tol=5e-6, what="G10 dx")
+    _close(yo2.grad, yq.grad, tol=5e-6, what="G10 dy")
     G = dict(meta=dict(torch=torch.__version__, note="projection heads: outputs of the unmodified reference, CPU fp32"),
-             G7=g7(pacl), G8=dict(y=yr.detach().clone(), dx=xr.grad.clone()))
+             G7=g7(pacl), G8=dict(y=yr.detach().clone(), dx=xr.grad.clone()), G9=ref_m,
+             G10=dict(loss=lq.detach().clone(), dx=xq.grad.clone(), dy=yq.grad.clone()))
     torch.save(G, os.path.join(OUT_DIR, "goldens_heads.pt"))
     print("G7 |y|", float(G["G7"]["y"].norm()), "|dx|", float(G["G7"]["dx"].norm()),
           "keys", sorted(G["G7"]["vis_sd"].keys()))

@@ -312,7 +312,8 @@ def apply_rope(embeddings):
 # ----------------------------------------------------------------------------
 def clip_metrics(image_features, text_features, logit_scale):
     """get_clip_metrics, open_clip/src/open_clip_train/train.py:360-377: descending argsort of the logits, position
-    of the ground truth, mean / median rank (+1), R@1/5/10.  Also returns the 0-based positions per direction."""
+    of the ground truth, mean / median rank (+1), R@1/5/10.  Also returns the 0-based positions per direction.
+    Pinned by golden G9 (the reference's own function, run by oracle/make_golden.py)."""
     import numpy as np
     logits_per_image = logit_scale * image_features @ text_features.t()
     out, preds_all = {}, {}
@@ -329,7 +330,7 @@ def clip_metrics(image_features, text_features, logit_scale):
 
 
 def simple_contrastive_loss(x, y, temperature=0.02, target=None, reduction="mean"):
-    """SimpleContrastiveLoss.__call__, VLM2Vec/src/loss.py:11-19."""
+    """SimpleContrastiveLoss.__call__, VLM2Vec/src/loss.py:11-19 (pinned by golden G10)."""
     if target is None:
         tpq = y.size(0) // x.size(0)
         target = torch.arange(0, x.size(0) * tpq, tpq, dtype=torch.long)

@@ -80,3 +80,29 @@ def make_sparc(pacl_mod, V, L, mask, sigma):
     s.forward_visual = lambda _images: V
     s.forward_text = lambda _caps: (L, mask)
     return s
+
+
+TRAIN_PY = os.path.join(REF_ROOT, "open_clip", "src", "open_clip_train", "train.py")
+VLM2VEC_LOSS_PY = os.path.join(REF_ROOT, "VLM2Vec", "src", "loss.py")
+
+
+def load_get_clip_metrics():
+    """The reference's own `get_clip_metrics` (open_clip_train/train.py:360-377).  The module cannot be imported here
+    (it pulls in the `open_clip` package), so the function's source is taken from the file with `ast` and executed
+    unmodified in a namespace that provides what it uses (torch, numpy)."""
+    import ast
+    import numpy as np
+    import torch
+    src = open(TRAIN_PY).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_clip_metrics")
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), TRAIN_PY, "exec"), ns)
+    return ns["get_clip_metrics"]
+
+
+def load_vlm2vec_loss():
+    """VLM2Vec/src/loss.py imports only torch: loaded by file path."""
+    if "vlm2vec_loss" not in _cache:
+        _cache["vlm2vec_loss"] = _load(VLM2VEC_LOSS_PY, "_ref_vlm2vec_loss")
+    return _cache["vlm2vec_loss"]

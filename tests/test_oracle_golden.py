@@ -116,3 +116,23 @@ def test_g8_rope():
     y = O.apply_rope(x)
     (y * O.rn(26, 2, 50, 64)).sum().backward()
     assert torch.allclose(y.detach(), G["y"], atol=1e-7) and torch.allclose(x.grad, G["dx"], atol=1e-7)
+
+
+def test_g9_g10_metrics_and_vlm2vec_loss():
+    """The reference's own get_clip_metrics (open_clip_train/train.py:360-377, executed unmodified from its source) and
+    VLM2Vec's SimpleContrastiveLoss (src/loss.py:7-19): the restatements reproduce their outputs."""
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)
+    gq = torch.Generator().manual_seed(77)
+    base = torch.randn(200, 32, generator=gq)
+    gi = O.l2n(base + 2.0 * torch.randn(200, 32, generator=gq))
+    gt = O.l2n(base + 2.0 * torch.randn(200, 32, generator=gq))
+    m, _ = O.clip_metrics(gi, gt, 100.0)
+    assert set(m) == set(G["G9"])
+    for k, v in G["G9"].items():
+        assert abs(float(m[k]) - v) < 1e-9, k
+    x, y = O.l2n(O.rn(28, 6, 16)).requires_grad_(), O.l2n(O.rn(29, 18, 16)).requires_grad_()
+    loss = O.simple_contrastive_loss(x, y, 0.02)
+    loss.backward()
+    assert abs(loss.item() - G["G10"]["loss"].item()) < 1e-5
+    assert rel_l2(x.grad, G["G10"]["dx"]) < 1e-5 and rel_l2(y.grad, G["G10"]["dy"]) < 1e-5
