@@ -114,3 +114,31 @@ def test_rope_matches_reference_golden():
     yb = apply_rope(xb.cuda())
     assert yb.dtype == torch.bfloat16
     assert rel_l2(yb.float().cpu(), O.apply_rope(xb.float())) < 4e-3
+
+
+def test_llm2pacl_c5_heads_to_eval_scorer():
+    """BASELINE configs[4] shape (LLM2PACL eval): 576 x 1024 patch tokens through LN + Patch_Projection(1024, 768), K
+    precomputed 4096-d LLM text embeddings through LN + Linear(4096, 768), then the one-launch eval scorer.
+    (1) given OUR head outputs, the scorer's top-1 is bit-exact against the fp32 oracle scorer on the same tensors;
+    (2) the heads themselves match the fp32 oracle heads to the bf16 tolerance; (3) end to end the top-1 agrees with the
+    all-fp32 oracle pipeline on at least 90 % of the items (bf16 heads can flip near-ties)."""
+    import clip_embeds_b200.functional as Fk
+    from clip_embeds_b200.heads import VisualProjection, TextProjection
+    items, K, P = 24, 4, 576
+    torch.manual_seed(11)
+    vis, txt = VisualProjection(1024, 768).eval(), TextProjection(4096, 768).eval()
+    sdv = {k: v.detach().clone() for k, v in vis.state_dict().items()}
+    sdt = {k: v.detach().clone() for k, v in txt.state_dict().items()}
+    patches, llm = O.rn(101, items, P, 1024), O.rn(102, items * K, 4096)
+    with torch.no_grad():
+        Vo, To = O.visual_projection(patches, sdv), O.text_projection(llm, sdt).reshape(items, K, 768)
+        top_o, _ = O.eval_top1(Vo, To, 100.0)
+        V = vis.cuda()(patches.cuda())
+        T = txt.cuda()(llm.cuda()).reshape(items, K, 768)
+        scores, top1 = Fk.pacl_eval_scores(V.float(), T.float())
+        top_same_inputs, _ = O.eval_top1(V.float().cpu(), T.float().cpu(), 100.0)
+    assert torch.equal(top1.cpu(), top_same_inputs)                                        # (1)
+    assert rel_l2(V.float().cpu(), Vo) < 2e-2 and rel_l2(T.float().cpu(), To) < 2e-2       # (2)
+    agree = (top1.cpu() == top_o).float().mean().item()
+    print(f"C5 heads -> eval scorer: top-1 agreement with the all-fp32 oracle pipeline {agree:.3f}")
+    assert agree >= 0.9                                                                    # (3)
