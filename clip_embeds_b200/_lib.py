@@ -25,9 +25,9 @@ SIGNATURES = {
                                       c_vp, c_vp]),
     "clipk_pacl_allpairs_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "clipk_pacl_allpairs_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
+                                        c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
     "clipk_pacl_allpairs_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
     "clipk_ce_rows": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "clipk_ce_cols": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "clipk_ce_rowsums": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),

@@ -216,7 +216,7 @@ struct PaclAct {
   struct Params {
     eng::OutDesc out;   // A
     const float* rnV;   // [batch][P]
-    const float* rnT;   // [M]
+    const float* rnT;   // [M], or nullptr when the A operand is already T^ = T rnT
     float* num;         // [batch][M] or nullptr
     int M, P, Ppad, act;
   };
@@ -225,7 +225,7 @@ struct PaclAct {
   __device__ explicit PaclAct(const Params& pp) : p(pp), rt(0.f), rt5(0.f), acc(0.f) {}
   __device__ void tile_begin(int, int m, int) {
     acc = 0.f;
-    rt = (m < p.M) ? __ldg(p.rnT + m) : 0.f;
+    rt = (m < p.M) ? (p.rnT != nullptr ? __ldg(p.rnT + m) : 1.f) : 0.f;
     rt5 = 5.f * rt;
   }
   __device__ Side pre(int b, int, int n) const {
@@ -304,6 +304,133 @@ struct Usq {
   __device__ void tile_end(int b, int m, int, int, int) {
     if (m < p.M) atomicAdd(p.usq + (int64_t)b * p.M + m, acc);
   }
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (fwd, saving u)
+// acc = u_ik[d];  usq[i,k] += sum_d u^2 (from the fp32 accumulator) and the pooled vector itself is stored as bf16
+// (TMA store) for the backward pass, which then needs neither the recompute of the activations' pooling GEMM nor a
+// per-group G scratch: the gradient factors (alpha, beta) are applied where u is consumed.
+struct UsqStore {
+  static constexpr bool kTmaOut = true;
+  struct Params {
+    eng::OutDesc out;   // U bf16 [batch][M][N]
+    float* usq;         // [batch][M]
+    int M, N;
+  };
+  Params p;
+  float acc;
+  __device__ explicit UsqStore(const Params& pp) : p(pp), acc(0.f) {}
+  __device__ void tile_begin(int, int, int) { acc = 0.f; }
+  __device__ void chunk(int, int, int n, float* v) {
+    if (n + 32 <= p.N) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < p.N) acc = fmaf(v[j], v[j], acc);
+    }
+  }
+  __device__ void tile_end(int b, int m, int, int, int) {
+    if (m < p.M) atomicAdd(p.usq + (int64_t)b * p.M + m, acc);
+  }
+};
+
+// ------------------------------------------------------------------------------------ PACL all-pairs, dual GEMM (bwd)
+// Two accumulators over the same V tile:  x = <T^_k, V_ip>  (A0 = T^ = bf16(T rnT))  and  d = <u_ik, V_ip>  (A1 = the
+// pooled vectors saved by the forward).  One pass produces everything the two gradient GEMMs need:
+//   s  = x rnV,  a = bf16(act(s))
+//   da = <G_ik, V_ip> = alpha x - beta d          (G = alpha t^ - beta u: gradient w.r.t. the un-normalised pooled vector)
+//   ds = da * act'(s)
+//   E  = ds rnV + alpha a        (out : operand of dt^ += E V  and of dV += E^T T^)
+//   A2 = -beta a                 (out2: operand of dV += A2^T U, the pooling term sum_k a G without its t^ part)
+//   dsdot[i,p] += sum_k ds * s   (= <v^_ip, dv^_ip>, the normalise-Jacobian projection)
+struct DsDual {
+  static constexpr bool kDual = true;
+  static constexpr bool kTmaOut = true;
+  static constexpr bool kTmaOut2 = true;
+  using Side = float;          // lane l holds rnV[i, n + l]
+  struct Params {
+    eng::OutDesc out;        // E  [batch][M][Ppad]
+    eng::OutDesc out2;       // A2 [batch][M][Ppad]
+    const float* rnV;        // [batch][P]
+    const float* alpha;      // [batch][M]
+    const float* beta;       // [batch][M]
+    float* dsdot;            // [batch][P]
+    int M, P, act;
+  };
+  Params p;
+  float al, nb;
+  __device__ explicit DsDual(const Params& pp) : p(pp), al(0.f), nb(0.f) {}
+  __device__ void tile_begin(int b, int m, int) {
+    al = (m < p.M) ? __ldg(p.alpha + (int64_t)b * p.M + m) : 0.f;
+    nb = (m < p.M) ? -__ldg(p.beta + (int64_t)b * p.M + m) : 0.f;
+  }
+  __device__ Side pre(int b, int, int n) const {
+    const int lane = (int)ptx::lane_id();
+    return (n + lane < p.P) ? __ldg(p.rnV + (int64_t)b * p.P + n + lane) : 0.f;
+  }
+  // in: x[] = <T^,V>, d[] = <u,V>;  out: x[] = E, d[] = A2
+  __device__ void chunk2(int b, int, int n, float* x, float* d, const Side& rn_l) {
+    const int lane = (int)ptx::lane_id();
+    const int col = n + lane;
+    if (p.act == CLIPK_ACT_ONES) {                       // warp-uniform: a = 1, ds = 0
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        x[j] = al;
+        d[j] = nb;
+      }
+      return;
+    }
+    float dss[32];
+    if (p.act == CLIPK_ACT_SOFTMAX10) {
+      // a = exp(10 (s - 1)),  ds = da * 10 a
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float r0 = __shfl_sync(0xffffffffu, rn_l, j);        // 0 for p >= P
+        const float r1 = __shfl_sync(0xffffffffu, rn_l, j + 1);
+        const float s0 = x[j] * r0, s1 = x[j + 1] * r1;
+        float a0 = ptx::ex2_approx(14.426950408889634f * (s0 - 1.f));
+        float a1 = ptx::ex2_approx(14.426950408889634f * (s1 - 1.f));
+        bf16_round_pair(a0, a1);
+        const float ds0 = fmaf(al, x[j], nb * d[j]) * 10.f * a0;
+        const float ds1 = fmaf(al, x[j + 1], nb * d[j + 1]) * 10.f * a1;
+        x[j] = fmaf(ds0, r0, al * a0);
+        x[j + 1] = fmaf(ds1, r1, al * a1);
+        d[j] = nb * a0;
+        d[j + 1] = nb * a1;
+        dss[j] = ds0 * s0;
+        dss[j + 1] = ds1 * s1;
+      }
+    } else {
+      // factors of 5 folded as in DsIn: r5 = 5 rnV, s5 = 5 s, ds5 = ds / 5 = da * 2 a (1 - a); E = alpha a + ds5 r5
+      const float r5_l = 5.f * rn_l;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float r0 = __shfl_sync(0xffffffffu, r5_l, j);
+        const float r1 = __shfl_sync(0xffffffffu, r5_l, j + 1);
+        const float s0 = x[j] * r0, s1 = x[j + 1] * r1;
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(s0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(s1));
+        float a0 = fmaf(0.5f, t0, 0.5f);
+        float a1 = fmaf(0.5f, t1, 0.5f);
+        bf16_round_pair(a0, a1);
+        const float u0 = a0 + a0, u1 = a1 + a1;
+        const float ds0 = fmaf(al, x[j], nb * d[j]) * fmaf(-u0, a0, u0);        // da * 2 a (1 - a)
+        const float ds1 = fmaf(al, x[j + 1], nb * d[j + 1]) * fmaf(-u1, a1, u1);
+        x[j] = fmaf(ds0, r0, al * a0);                                         // E
+        x[j + 1] = fmaf(ds1, r1, al * a1);
+        d[j] = nb * a0;                                                        // A2
+        d[j + 1] = nb * a1;
+        dss[j] = ds0 * s0;
+        dss[j + 1] = ds1 * s1;
+      }
+    }
+    const float cs = ptx::warp_colsum32(dss);   // lane j: sum over this warp's 32 rows of column n + j
+    if (col < p.P && cs != 0.f) atomicAdd(p.dsdot + (int64_t)b * p.P + col, cs);
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------ PACL all-pairs, GEMM2 (bwd)

@@ -104,7 +104,8 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
   constexpr bool TRANSPOSED = eng::epi_transposed<Epi>::value;
   static_assert(!TRANSPOSED || (CHUNK_IN && TMA_OUT && !TMA_OUT2), "transposed epilogues: chunk-in + one output");
   static_assert(!TMA_OUT2 || TMA_OUT, "a second output needs the first");
-  static_assert(!(TMA_OUT2 || CHUNK_IN) || (HAS_SIDE && !DUAL), "chunk-in / second output: uniform functors only");
+  static_assert(!CHUNK_IN || (HAS_SIDE && !DUAL), "chunk-in: uniform single-accumulator functors only");
+  static_assert(!TMA_OUT2 || HAS_SIDE, "second output: functors with side data only");
   static_assert(BN % 32 == 0 && BN <= 256, "BN: multiple of 32, at most 256");
   static_assert(!B_MN || (BN % 128 == 0), "MN-major B: each CTA's half must be whole 64-wide swizzle groups");
   static_assert(!DUAL || (BN <= 128 && !A_MN), "dual accumulators: BN <= 128, K-major A operands");
@@ -380,7 +381,7 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
           else epi.chunk2(b, m, n0 + c * 32, v, v1);
           PF_MARK(pf_math)
           if constexpr (HAS_SIDE) side = side_next;
-          store_chunk(v, nullptr, c);
+          store_chunk(v, v1, c);          // kTmaOut2: the functor left the second output chunk in v1
           ++slab;
         }
       } else {

@@ -123,10 +123,12 @@ struct LanePool {
   cudaEvent_t fork = nullptr, join[kMaxLanes] = {};
 };
 static int get_lanes(LanePool** out) {
-  static thread_local LanePool pools[8];
+  constexpr int kMaxDevices = 64;
+  static thread_local LanePool pools[kMaxDevices];
   int dev = 0;
   CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
-  LanePool& p = pools[dev & 7];
+  CLIPK_REQUIRE(dev >= 0 && dev < kMaxDevices, "pacl_allpairs: device ordinal %d out of range", dev);
+  LanePool& p = pools[dev];
   if (p.device != dev) {
     for (int i = 0; i < kMaxLanes; ++i) {
       CLIPK_CHECK_CUDA(cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking));
@@ -149,8 +151,10 @@ struct ApShared {
   __nv_bfloat16* That;
 };
 // layout: [lanes x per-lane scratch][shared per-call arrays]
+// `pooled`: the forward saves the pooled vectors u (bf16 [Bi,Bt,D], caller-owned) and the backward consumes them --
+// no G scratch, and the forward needs T^ as well (both directions use T^ = bf16(T rnT) as the score operand).
 static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt, int P, int D, int group, int lanes,
-                       int backward) {
+                       int backward, int pooled = 0) {
   const int Ppad = round_up(P, 64);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -163,7 +167,7 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
     w[l].A = static_cast<__nv_bfloat16*>(take(act));
     if (backward) {
       w[l].E = static_cast<__nv_bfloat16*>(take(act));
-      w[l].G = static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
+      w[l].G = pooled ? nullptr : static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
       w[l].dth = static_cast<float*>(take((size_t)kDthSplits * Bt * D * 4));
     }
   }
@@ -171,9 +175,9 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
     sh->dsdot = static_cast<float*>(take((size_t)Bi * P * 4));
     sh->alpha = static_cast<float*>(take((size_t)Bi * Bt * 4));
     sh->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
-    sh->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
     sh->dth = w[0].dth;
   }
+  if (backward || pooled) sh->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
   return off;
 }
 
@@ -266,6 +270,22 @@ static int join_lanes(LanePool* lp, int lanes, cudaStream_t st) {
   }
   return 0;
 }
+// Joins the forked lanes back into the caller's stream exactly once: explicitly on the success path (join()), and
+// from the destructor when a launch in between failed -- the caller's stream stays ordered after the lane streams
+// and a stream capture in progress is not left forked.
+struct LaneJoin {
+  LanePool* lp;
+  int lanes;
+  cudaStream_t st;
+  bool done = false;
+  int join() {
+    done = true;
+    return (lp != nullptr && lanes > 1) ? join_lanes(lp, lanes, st) : 0;
+  }
+  ~LaneJoin() {
+    if (!done && lp != nullptr && lanes > 1) (void)join_lanes(lp, lanes, st);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ mega path
 // One persistent kernel per direction (allpairs_mega.cuh).  `group` < 0: -group images per group; 0: automatic.
@@ -469,19 +489,27 @@ static int mega_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int 
 }
 
 int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
-                 float* rnV, float* rnT, float* num, float* usq, float* scores, void* ws, size_t ws_bytes, int group,
-                 int lanes, cudaStream_t st) {
+                 float* rnV, float* rnT, float* num, float* usq, float* scores, __nv_bfloat16* pooled, void* ws,
+                 size_t ws_bytes, int group, int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
-  if (group <= 0) return mega_fwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, scores, ws, ws_bytes, group, lanes, st);
+  if (group <= 0) {
+    CLIPK_REQUIRE(pooled == nullptr, "pacl_allpairs_fwd: the persistent kernel (group <= 0) does not save pooled vectors");
+    return mega_fwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, scores, ws, ws_bytes, group, lanes, st);
+  }
   CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
   ApWorkspace w[kMaxLanes]{};
   ApShared sh{};
-  const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0);
+  const int save = pooled != nullptr;
+  const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0, save);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
   rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
   rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
   count_launches(2);
+  if (save) {
+    that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
+    count_launches(1);
+  }
   CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
   LanePool* lp = nullptr;
@@ -490,20 +518,28 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     CLIPK_TRY(get_lanes(&lp));
     CLIPK_TRY(fork_lanes(lp, lanes, st));
   }
+  LaneJoin joiner{lp, lanes, st};      // joins the lanes on every exit path (error returns included)
   int gidx = 0;
   for (int i0 = 0; i0 < Bi; i0 += group, ++gidx) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
     const int l = gidx % lanes;
     cudaStream_t ls = lanes > 1 ? lp->st[l] : st;
     const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
-    CLIPK_TRY(launch_k1(T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, rnT, w[l], num + (int64_t)i0 * Bt, ls));
+    // pooled mode: the score operand is T^ (rnT folded in, as in the backward), so the epilogue's text norm is 1
+    CLIPK_TRY(launch_k1(save ? sh.That : T, V0, gi, Bt, P, D, act, rnV + (int64_t)i0 * P, save ? nullptr : rnT, w[l],
+                        num + (int64_t)i0 * Bt, ls));
     OperandDesc a, b;
     k2_operands(w[l], V0, gi, Bt, P, D, &a, &b);
     const int ks[1] = {Ppad / 64};
-    epi::Usq::Params ep{usq + (int64_t)i0 * Bt, Bt, D};
-    CLIPK_TRY(launch_nd<epi::Usq, false>((engine2_mask() & kK2) != 0, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+    if (save) {
+      epi::UsqStore::Params ep{{pooled + (int64_t)i0 * Bt * D, D, (int64_t)Bt * D, Bt, D, gi}, usq + (int64_t)i0 * Bt, Bt, D};
+      CLIPK_TRY(launch_nd<epi::UsqStore, false>(true, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+    } else {
+      epi::Usq::Params ep{usq + (int64_t)i0 * Bt, Bt, D};
+      CLIPK_TRY(launch_nd<epi::Usq, false>((engine2_mask() & kK2) != 0, &a, &b, 1, ks, ks, Bt, D, gi, ep, ls));
+    }
   }
-  if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
+  CLIPK_TRY(joiner.join());
   const int64_t n = (int64_t)Bi * Bt;
   allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
   count_launches(1);
@@ -511,10 +547,126 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   return 0;
 }
 
+// Backward from the saved pooled vectors (7 GEMM units per step instead of 8: no recompute of the pooling GEMM, no
+// separate recompute of the activations):
+//   B1  [x | d] = [T^ ; U_i] V_i^T   (dual accumulators, epilogue DsDual)  ->  E, A2 = -beta a, dsdot
+//   B2  dt^ += E V                   (K folds (image, patch), split-K slabs)
+//   B3  dV_i^T = U_i^T A2 + T^^T E - rnV^2 dsdot V^T   (two operand pairs, epilogue DvOutT)
+static int allpairs_bwd_pooled(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act,
+                               float c, const float* rnV, const float* rnT, const float* num, const float* usq,
+                               const float* dscores, const __nv_bfloat16* pooled, __nv_bfloat16* dV, float* dT, void* ws,
+                               size_t ws_bytes, int group, int lanes, cudaStream_t st) {
+  CLIPK_REQUIRE(group > 0, "pacl_allpairs_bwd: saved pooled vectors need the staged path (group > 0)");
+  CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
+  ApWorkspace wl[kMaxLanes]{};
+  ApShared sh{};
+  const size_t need = ap_carve(wl, &sh, ws, Bi, Bt, P, D, group, lanes, 1, 1);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int Ppad = round_up(P, 64);
+  const int64_t n = (int64_t)Bi * Bt;
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(sh.dsdot, 0, (size_t)Bi * P * 4, st));
+  for (int l = 0; l < lanes; ++l)
+    CLIPK_CHECK_CUDA(cudaMemsetAsync(wl[l].dth, 0, (size_t)kDthSplits * Bt * D * 4, st));
+  allpairs_alpha_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, dscores, n, c, sh.alpha, sh.beta);
+  that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
+  count_launches(2);
+  LanePool* lp = nullptr;
+  const PdlBlock no_pdl(lanes > 1);
+  if (lanes > 1) {
+    CLIPK_TRY(get_lanes(&lp));
+    CLIPK_TRY(fork_lanes(lp, lanes, st));
+  }
+  LaneJoin joiner{lp, lanes, st};
+  int gidx = 0;
+  for (int i0 = 0; i0 < Bi; i0 += group, ++gidx) {
+    const int gi = (Bi - i0) < group ? (Bi - i0) : group;
+    const int l = gidx % lanes;
+    const ApWorkspace& w = wl[l];
+    cudaStream_t ls = lanes > 1 ? lp->st[l] : st;
+    const __nv_bfloat16* V0 = V + (int64_t)i0 * P * D;
+    const __nv_bfloat16* U0 = pooled + (int64_t)i0 * Bt * D;
+    const float* rnV0 = rnV + (int64_t)i0 * P;
+    const float* alpha0 = sh.alpha + (int64_t)i0 * Bt;
+    const float* beta0 = sh.beta + (int64_t)i0 * Bt;
+    float* dsdot0 = sh.dsdot + (int64_t)i0 * P;
+    // B1: dual GEMM over V_i: x = T^ V^T, d = U V^T  ->  E, A2, dsdot
+    {
+      OperandDesc a[2], b;
+      a[0].ptr = sh.That; a[0].rows = Bt; a[0].k = D; a[0].ld = D; a[0].batch = 1; a[0].bmul = 0;
+      a[1].ptr = U0; a[1].rows = Bt; a[1].k = D; a[1].ld = D; a[1].batch = gi; a[1].batch_stride = (int64_t)Bt * D; a[1].bmul = 1;
+      b.ptr = V0; b.rows = P; b.k = D; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 1;
+      const int ks[1] = {(D + 63) / 64};
+      const eng::OutDesc oe{w.E, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // extent P: pad columns clipped on store,
+      const eng::OutDesc oa{w.A, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // zero-filled on load
+      epi::DsDual::Params ep{oe, oa, rnV0, alpha0, beta0, dsdot0, Bt, P, act};
+      if (Ppad >= 128) CLIPK_TRY((launch_gemm2<128, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
+      else CLIPK_TRY((launch_gemm2<64, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
+    }
+    // B2: dt^[k, :] += sum_{i,p} E[i,k,p] V[i,p,:]   (split-K over images into fp32 slabs, summed in the finalize)
+    {
+      const int want = gi < kDthSplits ? gi : kDthSplits;
+      const int spb = (gi + want - 1) / want;
+      const int nsplit = (gi + spb - 1) / spb;
+      OperandDesc a, b;
+      a.ptr = w.E; a.rows = Bt; a.k = P; a.ld = Ppad; a.batch = gi; a.batch_stride = (int64_t)Bt * Ppad; a.bmul = 0; a.smul = 1;
+      a.sub_per_batch = spb;
+      a.sub_total = gi;
+      a.reverse = 1;   // B1 walked upwards: take the last-written E first
+      b.ptr = V0; b.mn_major = true; b.rows = D; b.k = P; b.ld = D; b.batch = gi; b.batch_stride = (int64_t)P * D; b.bmul = 0; b.smul = 1;
+      const int ks[1] = {spb * (Ppad / 64)};
+      const int ksub[1] = {Ppad / 64};
+      epi::Store<false>::Params ep{w.dth, D, (int64_t)Bt * D, Bt, D, 1.f, 1};
+      CLIPK_TRY(launch_nd<epi::Store<false>, false>(true, &a, &b, 1, ks, ksub, Bt, D, nsplit, ep, ls));
+    }
+    // B3: dV_i = A2_i^T U_i + E_i^T T^ - rnV^2 dsdot V, in the orientation that wastes less of the 256-row tiles
+    {
+      const bool transposed = env_int("CLIPK_AP_K6T", 1) != 0 && D % 8 == 0 &&
+                              (int64_t)round_up(D, 256) * round_up(P, 16) < (int64_t)round_up(P, 256) * round_up(D, 16);
+      const int ks[2] = {(Bt + 63) / 64, (Bt + 63) / 64};
+      if (transposed) {
+        OperandDesc a[2], b[2];
+        a[0].ptr = U0; a[0].mn_major = true; a[0].rows = D; a[0].k = Bt; a[0].ld = D; a[0].batch = gi;
+        a[0].batch_stride = (int64_t)Bt * D; a[0].bmul = 1;
+        a[0].reverse = 1;
+        b[0].ptr = w.A; b[0].mn_major = true; b[0].rows = P; b[0].k = Bt; b[0].ld = Ppad; b[0].batch = gi;
+        b[0].batch_stride = (int64_t)Bt * Ppad; b[0].bmul = 1;
+        a[1].ptr = sh.That; a[1].mn_major = true; a[1].rows = D; a[1].k = Bt; a[1].ld = D; a[1].batch = 1; a[1].bmul = 0;
+        b[1] = b[0]; b[1].ptr = w.E;
+        const eng::OutDesc odv{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi};
+        const eng::OutDesc ov{const_cast<__nv_bfloat16*>(V0), D, (int64_t)P * D, P, D, gi};
+        epi::DvOutT::Params ep{odv, ov, rnV0, dsdot0, P};
+        CLIPK_TRY((launch_gemm2<256, true, true, epi::DvOutT>(a, b, 2, ks, ks, D, P, gi, ep, ls)));
+      } else {
+        OperandDesc a[2], b[2];
+        a[0].ptr = w.A; a[0].mn_major = true; a[0].rows = P; a[0].k = Bt; a[0].ld = Ppad; a[0].batch = gi;
+        a[0].batch_stride = (int64_t)Bt * Ppad; a[0].bmul = 1;
+        a[0].reverse = 1;
+        b[0].ptr = U0; b[0].mn_major = true; b[0].rows = D; b[0].k = Bt; b[0].ld = D; b[0].batch = gi;
+        b[0].batch_stride = (int64_t)Bt * D; b[0].bmul = 1;
+        a[1] = a[0]; a[1].ptr = w.E;
+        b[1].ptr = sh.That; b[1].mn_major = true; b[1].rows = D; b[1].k = Bt; b[1].ld = D; b[1].batch = 1; b[1].bmul = 0;
+        epi::DvOut::Params ep{{dV + (int64_t)i0 * P * D, D, (int64_t)P * D, P, D, gi}, V0, rnV0, dsdot0, P, D};
+        CLIPK_TRY(launch_nd<epi::DvOut, true>(true, a, b, 2, ks, ks, P, D, gi, ep, ls));
+      }
+    }
+  }
+  CLIPK_TRY(joiner.join());
+  DthSlabs slabs{};
+  for (int l = 0; l < lanes; ++l) slabs.p[l] = wl[l].dth;
+  dtext_finalize_kernel<<<Bt, 256, 0, st>>>(T, rnT, slabs, lanes, kDthSplits, Bt, D, dT);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  const float* rnV, const float* rnT, const float* num, const float* usq, const float* dscores,
-                 __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group, int lanes, cudaStream_t st) {
+                 const __nv_bfloat16* pooled, __nv_bfloat16* dV, float* dT, void* ws, size_t ws_bytes, int group,
+                 int lanes, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
+  if (pooled != nullptr)
+    return allpairs_bwd_pooled(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, dscores, pooled, dV, dT, ws, ws_bytes,
+                               group, lanes, st);
   if (group <= 0)
     return mega_bwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, dscores, dV, dT, ws, ws_bytes, group, lanes, st);
   CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
@@ -536,6 +688,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
     CLIPK_TRY(get_lanes(&lp));
     CLIPK_TRY(fork_lanes(lp, lanes, st));
   }
+  LaneJoin joiner{lp, lanes, st};
   int gidx = 0;
   for (int i0 = 0; i0 < Bi; i0 += group, ++gidx) {
     const int gi = (Bi - i0) < group ? (Bi - i0) : group;
@@ -636,7 +789,7 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
       }
     }
   }
-  if (lanes > 1) CLIPK_TRY(join_lanes(lp, lanes, st));
+  CLIPK_TRY(joiner.join());
   DthSlabs slabs{};
   for (int l = 0; l < lanes; ++l) slabs.p[l] = wl[l].dth;
   dtext_finalize_kernel<<<Bt, 256, 0, st>>>(T, rnT, slabs, lanes, kDthSplits, Bt, D, dT);
@@ -649,7 +802,8 @@ int allpairs_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
 
 extern "C" {
 
-size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int backward) {
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int mode) {
+  const int backward = mode & 1, pooled = (mode >> 1) & 1;
   if (group <= 0) {
     clipk::MegaWs mw{};
     return clipk::mega_carve(&mw, nullptr, clipk::mega_plan(Bi, Bt, P, D, group, lanes, backward), Bi, Bt, P, D, backward);
@@ -657,25 +811,26 @@ size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int gro
   clipk::ApWorkspace w[clipk::kMaxLanes]{};
   clipk::ApShared sh{};
   if (lanes < 1 || lanes > clipk::kMaxLanes) return 0;
-  return clipk::ap_carve(w, &sh, nullptr, Bi, Bt, P, D, group, lanes, backward);
+  return clipk::ap_carve(w, &sh, nullptr, Bi, Bt, P, D, group, lanes, backward, pooled);
 }
 
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
-                            float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
-                            int group, int lanes, void* stream) {
+                            float* rnT, float* num, float* usq, float* scores, void* pooled, void* workspace,
+                            size_t ws_bytes, int group, int lanes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::allpairs_fwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
-                             act, c, rnV, rnT, num, usq, scores, workspace, ws_bytes, group, lanes,
-                             static_cast<cudaStream_t>(stream));
+                             act, c, rnV, rnT, num, usq, scores, static_cast<__nv_bfloat16*>(pooled), workspace,
+                             ws_bytes, group, lanes, static_cast<cudaStream_t>(stream));
 }
 
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
                             const float* rnV, const float* rnT, const float* num, const float* usq,
-                            const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
-                            int lanes, void* stream) {
+                            const float* dscores, const void* pooled, void* dV, float* dT, void* workspace,
+                            size_t ws_bytes, int group, int lanes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::allpairs_bwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
-                             act, c, rnV, rnT, num, usq, dscores, static_cast<__nv_bfloat16*>(dV), dT, workspace,
-                             ws_bytes, group, lanes, static_cast<cudaStream_t>(stream));
+                             act, c, rnV, rnT, num, usq, dscores, static_cast<const __nv_bfloat16*>(pooled),
+                             static_cast<__nv_bfloat16*>(dV), dT, workspace, ws_bytes, group, lanes,
+                             static_cast<cudaStream_t>(stream));
 }
 }

@@ -142,6 +142,18 @@ def _resolve(group, Bi, Bt, P, D, backward):
     return max(1, min(g, Bi)), max(1, min(lanes, 4))
 
 
+# The forward may keep the un-normalised pooled vectors u_ik (bf16 [Bi,Bt,D]) for the backward pass, which then needs
+# 5 GEMM units instead of 6 (no recompute of activations + pooling).  Budget in bytes per call; above it (or with
+# CLIPK_AP_SAVE_POOLED=0) the backward recomputes (flash-style, O(Bi*Bt) statistics only).
+_POOLED_BUDGET = int(float(os.environ.get("CLIPK_AP_POOLED_BUDGET_GB", "48")) * (1 << 30))
+
+
+def _save_pooled(Bi, Bt, D, g, needs_grad):
+    if not needs_grad or g <= 0 or os.environ.get("CLIPK_AP_SAVE_POOLED", "1") == "0":
+        return False
+    return Bi * Bt * D * 2 <= _POOLED_BUDGET
+
+
 class _PaclAllPairs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, T, c, act, group):
@@ -152,21 +164,32 @@ class _PaclAllPairs(torch.autograd.Function):
         Bt = Tb.shape[0]
         dev = Vb.device
         g, lanes = _resolve(group, Bi, Bt, P, D, False)
+        needs_grad = any(ctx.needs_input_grad[:2])
+        gb, _ = _resolve(group, Bi, Bt, P, D, True)
+        save = _save_pooled(Bi, Bt, D, min(g, gb), needs_grad)
         rnV, rnT = _f32(Bi, P, device=dev), _f32(Bt, device=dev)
         num, usq, scores = _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev)
-        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 0)
+        pooled = torch.empty(Bi, Bt, D, dtype=torch.bfloat16, device=dev) if save else None
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 2 if save else 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_pacl_allpairs_fwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
-                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), ws.data_ptr(), nbytes, g, lanes,
-                  _stream())
-        ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq)
-        ctx.cfg = (c, act, group, V.dtype, T.dtype)
+                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), _p(pooled), ws.data_ptr(), nbytes,
+                  g, lanes, _stream())
+        if save:
+            ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq, pooled)
+        else:
+            ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq)
+        ctx.cfg = (c, act, group, V.dtype, T.dtype, save)
         return scores
 
     @staticmethod
     def backward(ctx, dscores):
-        Vb, Tb, rnV, rnT, num, usq = ctx.saved_tensors
-        c, act, group, v_dtype, t_dtype = ctx.cfg
+        c, act, group, v_dtype, t_dtype, save = ctx.cfg
+        if save:
+            Vb, Tb, rnV, rnT, num, usq, pooled = ctx.saved_tensors
+        else:
+            Vb, Tb, rnV, rnT, num, usq = ctx.saved_tensors
+            pooled = None
         Bi, P, D = Vb.shape
         Bt = Tb.shape[0]
         dev = Vb.device
@@ -174,11 +197,11 @@ class _PaclAllPairs(torch.autograd.Function):
         dscores = dscores.float().contiguous()
         dV = torch.empty_like(Vb)
         dT = _f32(Bt, D, device=dev)
-        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 1)
+        nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 3 if save else 1)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_pacl_allpairs_bwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
-                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), dscores.data_ptr(), dV.data_ptr(), dT.data_ptr(),
-                  ws.data_ptr(), nbytes, g, lanes, _stream())
+                  rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), dscores.data_ptr(), _p(pooled), dV.data_ptr(),
+                  dT.data_ptr(), ws.data_ptr(), nbytes, g, lanes, _stream())
         return dV.to(v_dtype), dT.to(t_dtype), None, None, None
 
 

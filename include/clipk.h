@@ -86,16 +86,20 @@ int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P,
  * Saved for backward (caller-owned): rnV [Bi,P], rnT [Bt], num [Bi,Bt], usq [Bi,Bt].  The [Bi,Bt,P] activations
  * only ever exist for `group` images per lane inside `workspace` (tcgen05 GEMMs with fused epilogues); image groups
  * are issued round-robin on `lanes` (1..4) internal streams forked from / joined to `stream` with events.
+ * `pooled` (nullable, bf16 [Bi,Bt,D], caller-owned): when given, the forward also stores the un-normalised pooled
+ * vectors u_ik and the backward reads them instead of recomputing activations + pooling (7 GEMM units per step
+ * instead of 8; SURVEY 7.3-5 "store U as bf16").  Pass the same buffer (or NULL both times) to fwd and bwd.
  * Backward: dscores [Bi,Bt] -> dV bf16 [Bi,P,D], dT fp32 [Bt,D] (gradient w.r.t. the raw T).
+ * workspace_bytes `mode`: bit 0 = backward, bit 1 = pooled.
  */
-size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int backward);
+size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int mode);
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
-                            float* rnT, float* num, float* usq, float* scores, void* workspace, size_t ws_bytes,
-                            int group, int lanes, void* stream);
+                            float* rnT, float* num, float* usq, float* scores, void* pooled, void* workspace,
+                            size_t ws_bytes, int group, int lanes, void* stream);
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
                             const float* rnV, const float* rnT, const float* num, const float* usq,
-                            const float* dscores, void* dV, float* dT, void* workspace, size_t ws_bytes, int group,
-                            int lanes, void* stream);
+                            const float* dscores, const void* pooled, void* dV, float* dT, void* workspace,
+                            size_t ws_bytes, int group, int lanes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Cross-entropy over a materialised fp32 matrix L [M,N] (leading dim ld): F.cross_entropy at pacl.py:509-512,
