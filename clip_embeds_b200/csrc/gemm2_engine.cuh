@@ -180,21 +180,31 @@ gemm2_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const t
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(&full_bar[0]), 0);   // shared::cluster address in the leader
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const TileCoord tc = tile_coord<BN>(pb, tile, total_tiles, tiles_per_batch, rank);
         const int nb0 = tc.n0 + rank * (tile_ncols<BN>(pb, tc.n0) >> 1);   // first B row of this CTA's half
         for (int q = 0; q < pb.num_pairs; ++q) {
           const int nks = ksteps_of(pb, q, tc.b);
+          // No integer division in this loop: on this single thread each one costs ~150 cycles, which (with the barrier
+          // wait and the TMA issues) bounded the ring at ~500 cycles per k-step -- above the 384 / 256 cycles an N = 192 /
+          // 128 k-step of MMAs takes.  `subl` / `kin` split ks = subl * ksub + kin incrementally.
+          int subl = 0, kin = 0;
+          const int ksub = pb.ksub[q];
+          const int kbase = tc.b * pb.k_boff[q];
+          const int sub0 = tc.b * pb.sub_per_batch[q];
+          const int ab0 = tc.b * pb.a_bmul[q], bb0 = tc.b * pb.b_bmul[q];
+          const int asm_ = pb.a_smul[q], bsm_ = pb.b_smul[q];
           for (int ks = 0; ks < nks; ++ks) {
-            const int subl = ks / pb.ksub[q];
-            const int k0 = (ks - subl * pb.ksub[q]) * BK + tc.b * pb.k_boff[q];
-            const int sub = subl + tc.b * pb.sub_per_batch[q];
-            const int ab = tc.b * pb.a_bmul[q] + sub * pb.a_smul[q];
-            const int bb = tc.b * pb.b_bmul[q] + sub * pb.b_smul[q];
+            const int k0 = kin * BK + kbase;
+            const int sub = subl + sub0;
+            const int ab = ab0 + sub * asm_;
+            const int bb = bb0 + sub * bsm_;
+            if (++kin == ksub) { kin = 0; ++subl; }
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
-            const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            const uint32_t fb = full_leader0 + static_cast<uint32_t>(stage) * 8u;
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
             if constexpr (DUAL) {
               const int ab1 = tc.b * pb.a_bmul[1];

@@ -201,6 +201,8 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
       struct Cursor {
         int tile, q, ks, nks, b, m0, n0;
         bool valid;
+        int subl, kin;      // ks = subl * ksub + kin, maintained incrementally: an integer division per k-step costs this
+                            // single thread ~150 cycles, which is what bounded the ring at ~500 cycles per k-step
       };
       auto seek = [&](Cursor& c) {   // position on the first k-step of (tile, q), skipping empty ranges
         while (c.tile < total_tiles) {
@@ -214,20 +216,25 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
             if (c.ks < c.nks) { c.valid = true; return; }
             ++c.q;
             c.ks = 0;
+            c.subl = 0;
+            c.kin = 0;
           }
           c.tile += gridDim.x;
           c.q = 0;
           c.ks = 0;
+          c.subl = 0;
+          c.kin = 0;
         }
         c.valid = false;
       };
       auto advance = [&](Cursor& c) {
         ++c.ks;
+        if (++c.kin == pb.ksub[c.q]) { c.kin = 0; ++c.subl; }
         if (c.ks >= c.nks) seek(c);
       };
       auto coords = [&](const Cursor& c, int& k0, int& ab, int& bb) {
-        const int subl = c.ks / pb.ksub[c.q];
-        k0 = (c.ks - subl * pb.ksub[c.q]) * BK;
+        const int subl = c.subl;
+        k0 = c.kin * BK;
         const int sub = subl + c.b * pb.sub_per_batch[c.q];
         ab = c.b * pb.a_bmul[c.q] + sub * pb.a_smul[c.q];
         bb = c.b * pb.b_bmul[c.q] + sub * pb.b_smul[c.q];
@@ -248,7 +255,7 @@ gemm_kernel(const __grid_constant__ OperandMaps maps, const Problem pb, const ty
           for (int j = 0; j < BN / 64; ++j) ptx::tma_prefetch_3d(&maps.b[c.q], c.n0 + j * 64, k0, bb);
         }
       };
-      Cursor ld{(int)blockIdx.x, 0, 0, 0, 0, 0, 0, false};
+      Cursor ld{(int)blockIdx.x, 0, 0, 0, 0, 0, 0, false, 0, 0};
       seek(ld);
       Cursor pf = ld;
       for (int i = 0; i < kPrefetchDist && pf.valid; ++i) {

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "allpairs_mega.cuh"
+#include "pacl_fused.cuh"
 #include "simt_util.cuh"
 
 namespace clipk {
@@ -154,7 +155,7 @@ struct ApShared {
 // `pooled`: the forward saves the pooled vectors u (bf16 [Bi,Bt,D], caller-owned) and the backward consumes them --
 // no G scratch, and the forward needs T^ as well (both directions use T^ = bf16(T rnT) as the score operand).
 static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt, int P, int D, int group, int lanes,
-                       int backward, int pooled = 0) {
+                       int backward, int pooled = 0, int fused_fwd = 0) {
   const int Ppad = round_up(P, 64);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -164,7 +165,7 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
   };
   const size_t act = (size_t)group * Bt * Ppad * 2;
   for (int l = 0; l < lanes; ++l) {
-    w[l].A = static_cast<__nv_bfloat16*>(take(act));
+    w[l].A = (!backward && fused_fwd) ? nullptr : static_cast<__nv_bfloat16*>(take(act));   // fused forward: activations stay on chip
     if (backward) {
       w[l].E = static_cast<__nv_bfloat16*>(take(act));
       w[l].G = pooled ? nullptr : static_cast<__nv_bfloat16*>(take((size_t)group * Bt * D * 2));
@@ -177,7 +178,7 @@ static size_t ap_carve(ApWorkspace* w, ApShared* sh, void* base, int Bi, int Bt,
     sh->beta = static_cast<float*>(take((size_t)Bi * Bt * 4));
     sh->dth = w[0].dth;
   }
-  if (backward || pooled) sh->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
+  if (backward || pooled || fused_fwd) sh->That = static_cast<__nv_bfloat16*>(take((size_t)Bt * D * 2));
   return off;
 }
 
@@ -488,6 +489,65 @@ static int mega_bwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ fused forward
+// One persistent launch for the whole forward (pacl_fused.cuh): activations never leave the SM.  Shapes it covers:
+// P <= 576 (the activations of 128 texts x P patches are resident in shared memory) and D a multiple of 128; anything
+// else takes the staged path below.  CLIPK_AP_FUSED=0 forces the staged path (A/B diagnostics).
+static bool fused_fwd_eligible(int P, int D) {
+  return P <= 64 * fz::kMaxKB && D >= 128 && D % 128 == 0 && env_int("CLIPK_AP_FUSED", 1) != 0;
+}
+
+template <bool SAVE_U>
+static int fused_fwd_launch(const __nv_bfloat16* V, const __nv_bfloat16* That, int Bi, int Bt, int P, int D, int act,
+                            const float* rnV, float* num, float* usq, __nv_bfloat16* pooled, cudaStream_t st) {
+  fz::Params pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.Bi = Bi; pr.Bt = Bt; pr.P = P; pr.D = D; pr.act = act;
+  if (P <= 256) {
+    pr.nS = 1;
+    pr.pc = round_up(P, 16);
+  } else {
+    pr.nS = (P + 255) / 256;
+    pr.pc = round_up((P + pr.nS - 1) / pr.nS, 64);
+    pr.nS = (P + pr.pc - 1) / pr.pc;
+  }
+  pr.nU = (D + 255) / 256;
+  pr.kbA = (P + 63) / 64;
+  pr.ksD = (D + 63) / 64;
+  pr.tilesM = (Bt + 255) / 256;
+  pr.rnV = rnV; pr.num = num; pr.usq = usq;
+  pr.pooled = pooled;
+  pr.V = V;
+  pr.prefetch = env_int("CLIPK_FZ_PREFETCH", 1);
+  pr.xslots = env_int("CLIPK_FZ_XSLOTS", 1);
+  CLIPK_REQUIRE(pr.nS <= fz::kMaxChunks && pr.pc <= 256 && pr.kbA <= fz::kMaxKB, "pacl fused forward: P=%d out of range", P);
+  fz::Maps mp;
+  memset(&mp, 0, sizeof(mp));
+  const uint64_t ldD = (uint64_t)D * 2;
+  CLIPK_TRY(make_tmap_bf16(&mp.T, That, D, Bt, 1, ldD, 0, 128));
+  CLIPK_TRY(make_tmap_bf16(&mp.Vk, V, D, P, Bi, ldD, (uint64_t)P * ldD, (uint32_t)(pr.pc / 2)));
+  CLIPK_TRY(make_tmap_bf16(&mp.Vmn, V, D, P, Bi, ldD, (uint64_t)P * ldD, 64));
+  auto kern = fz::pacl_fused_fwd_kernel<SAVE_U>;
+  constexpr int kSmem = fz::kSmemTotal;
+  static std::atomic<uint64_t> attr_mask{0};
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  const int nitems = Bi * pr.tilesM;
+  const int pairs = sm_count() / 2;
+  const int grid = 2 * (nitems < pairs ? nitems : pairs);
+  const bool tr = trace_enabled();
+  if (tr) trace_begin(SAVE_U ? "pacl_fused_fwd_kernel<save pooled>" : "pacl_fused_fwd_kernel", st);
+  kern<<<grid, fz::kThreads, kSmem, st>>>(mp, pr);
+  if (tr) trace_end(st);
+  count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  float* rnV, float* rnT, float* num, float* usq, float* scores, __nv_bfloat16* pooled, void* ws,
                  size_t ws_bytes, int group, int lanes, cudaStream_t st) {
@@ -500,18 +560,28 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   ApWorkspace w[kMaxLanes]{};
   ApShared sh{};
   const int save = pooled != nullptr;
-  const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0, save);
+  const bool fused = fused_fwd_eligible(P, D);
+  const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0, save, fused);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
   rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
   rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
   count_launches(2);
-  if (save) {
+  if (save || fused) {
     that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
     count_launches(1);
   }
   CLIPK_CHECK_CUDA(cudaMemsetAsync(num, 0, (size_t)Bi * Bt * 4, st));
   CLIPK_CHECK_CUDA(cudaMemsetAsync(usq, 0, (size_t)Bi * Bt * 4, st));
+  if (fused) {
+    if (save) CLIPK_TRY(fused_fwd_launch<true>(V, sh.That, Bi, Bt, P, D, act, rnV, num, usq, pooled, st));
+    else CLIPK_TRY(fused_fwd_launch<false>(V, sh.That, Bi, Bt, P, D, act, rnV, num, usq, nullptr, st));
+    const int64_t n = (int64_t)Bi * Bt;
+    allpairs_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num, usq, n, c, scores);
+    count_launches(1);
+    CLIPK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   LanePool* lp = nullptr;
   const PdlBlock no_pdl(lanes > 1);
   if (lanes > 1) {
@@ -811,7 +881,8 @@ size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int gro
   clipk::ApWorkspace w[clipk::kMaxLanes]{};
   clipk::ApShared sh{};
   if (lanes < 1 || lanes > clipk::kMaxLanes) return 0;
-  return clipk::ap_carve(w, &sh, nullptr, Bi, Bt, P, D, group, lanes, backward, pooled);
+  return clipk::ap_carve(w, &sh, nullptr, Bi, Bt, P, D, group, lanes, backward, pooled,
+                         !backward && clipk::fused_fwd_eligible(P, D));
 }
 
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,

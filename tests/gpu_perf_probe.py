@@ -140,12 +140,13 @@ if __name__ == "__main__":
         allpairs_once(B, 576, 768, grp)
         _lib.lib().clipk_trace_dump()
     if cmd == "fwdonce":
-        V = torch.randn(int(sys.argv[2]), 576, 768, device="cuda").to(torch.bfloat16)
+        V = torch.randn(int(sys.argv[2]), int(os.environ.get("PROBE_P", "576")), 768, device="cuda").to(torch.bfloat16)
         T = torch.randn(1024, 768, device="cuda").to(torch.bfloat16)
         with torch.no_grad():
             a = sys.argv[3]
-            Fk.pacl_scores(V, T, 10.0, "sigmoid", tuple(int(y) for y in a.split(":")) if ":" in a else int(a))
-        torch.cuda.synchronize()
+            for _ in range(int(os.environ.get("PROBE_REPEAT", "1"))):
+                Fk.pacl_scores(V, T, 10.0, "sigmoid", tuple(int(y) for y in a.split(":")) if ":" in a else int(a))
+                torch.cuda.synchronize()
     if cmd == "cpu":
         import time
         B = 1024
