@@ -290,6 +290,20 @@ sgemm128_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, c
 // ------------------------------------------------------------------------------------------------ (3) engine CE
 namespace epi {
 
+// number of existing columns among [n, n + 32) (warp-uniform): the matrix edge N and, past slab_n0, the fill count of
+// the hard-negative slab the chunk lies in (chunks do not straddle slabs: slab_n0 and slab_rows are multiples of 32)
+__device__ __forceinline__ int chunk_valid_cols(int n, int N, const int* slab_counts, int slab_n0, int slab_rows) {
+  int lim = N - n;
+  lim = lim < 32 ? lim : 32;
+  if (slab_counts != nullptr && n >= slab_n0) {
+    const int off = n - slab_n0;
+    const int r = off / slab_rows;
+    const int left = __ldg(slab_counts + r) - (off - r * slab_rows);
+    lim = left < lim ? left : lim;
+  }
+  return lim < 0 ? 0 : lim;
+}
+
 // per-(row, n-tile) online log-sum-exp partial of logits = scale * acc + bias; captures the label logit.
 struct LsePart {
   struct Params {
@@ -299,11 +313,19 @@ struct LsePart {
     int64_t label_offset;
     int M, N, tiles_n;
     float scale, bias;
+    const float* scale_dev;  // nullable: logit scale read from device memory (open_clip passes logit_scale.exp() as a tensor)
+    // Fixed-capacity hard-negative slabs (loss.py:67-87 without the host-side size exchange): columns >= slab_n0 are W
+    // slabs of `slab_rows` rows each, of which only the first slab_counts[r] exist; the others are masked out
+    // (logit = -inf).  slab_counts == nullptr: every column exists.
+    const int* slab_counts;
+    int slab_n0, slab_rows;
   };
   Params p;
   float mx, sm;
   int64_t lab;
-  __device__ explicit LsePart(const Params& pp) : p(pp), mx(0.f), sm(0.f), lab(-1) {}
+  __device__ explicit LsePart(const Params& pp) : p(pp), mx(0.f), sm(0.f), lab(-1) {
+    if (p.scale_dev != nullptr) p.scale = __ldg(p.scale_dev);
+  }
   __device__ void tile_begin(int, int m, int) {
     mx = -INFINITY;
     sm = 0.f;
@@ -312,17 +334,19 @@ struct LsePart {
   }
   __device__ void chunk(int, int m, int n, float* v) {
     if (m >= p.M || n >= p.N) return;
+    const int lim = chunk_valid_cols(n, p.N, p.slab_counts, p.slab_n0, p.slab_rows);
+    if (lim <= 0) return;
     float cm = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       v[j] = fmaf(v[j], p.scale, p.bias);
-      if (n + j < p.N) cm = fmaxf(cm, v[j]);
+      if (j < lim) cm = fmaxf(cm, v[j]);
     }
     const float nm = fmaxf(mx, cm);
     float acc = sm * __expf(mx - nm);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (n + j < p.N) acc += __expf(v[j] - nm);
+      if (j < lim) acc += __expf(v[j] - nm);
     sm = acc;
     mx = nm;
     if (lab >= n && lab < (int64_t)n + 32 && lab < p.N) {
@@ -349,11 +373,16 @@ struct DlOut {
     int64_t ldd;
     int M, N;
     float scale, bias;
+    const float* scale_dev;  // nullable
+    const int* slab_counts;  // see LsePart
+    int slab_n0, slab_rows;
   };
   Params p;
   float lse, w;
   int64_t lab;
-  __device__ explicit DlOut(const Params& pp) : p(pp), lse(0.f), w(0.f), lab(-1) {}
+  __device__ explicit DlOut(const Params& pp) : p(pp), lse(0.f), w(0.f), lab(-1) {
+    if (p.scale_dev != nullptr) p.scale = __ldg(p.scale_dev);
+  }
   __device__ void tile_begin(int, int m, int) {
     if (m < p.M) {
       lse = p.lse[m];
@@ -363,11 +392,12 @@ struct DlOut {
   }
   __device__ void chunk(int, int m, int n, float* v) {
     if (m >= p.M || n >= p.N) return;
+    const int lim = chunk_valid_cols(n, p.N, p.slab_counts, p.slab_n0, p.slab_rows);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float l = fmaf(v[j], p.scale, p.bias);
       const float hit = ((int64_t)(n + j) == lab) ? 1.f : 0.f;
-      v[j] = (w == 0.f) ? 0.f : w * (__expf(l - lse) - hit);
+      v[j] = (w == 0.f || j >= lim) ? 0.f : w * (__expf(l - lse) - hit);
     }
     store_bf16x32(p.dL + (int64_t)m * p.ldd + n, v, min(32, p.N - n));
   }
@@ -386,11 +416,16 @@ struct DlOutTma {
     int64_t label_offset;
     int M, N;
     float scale, bias;
+    const float* scale_dev;  // nullable
+    const int* slab_counts;  // see LsePart
+    int slab_n0, slab_rows;
   };
   Params p;
   float nlse, w;
   int lab;                   // label column of this row, or -1
-  __device__ explicit DlOutTma(const Params& pp) : p(pp), nlse(0.f), w(0.f), lab(-1) {}
+  __device__ explicit DlOutTma(const Params& pp) : p(pp), nlse(0.f), w(0.f), lab(-1) {
+    if (p.scale_dev != nullptr) p.scale = __ldg(p.scale_dev);
+  }
   __device__ void tile_begin(int, int m, int) {
     w = 0.f;
     nlse = 0.f;
@@ -405,8 +440,9 @@ struct DlOutTma {
   __device__ void chunk(int, int, int n, float* v) {
     // w (exp(logit - lse) - [n + j == label]);  rows with w == 0 (ignored rows, rows past M) give exact zeros
     const float k2 = p.scale * 1.4426950408889634f, c2 = nlse * 1.4426950408889634f;
+    const int lim = p.slab_counts != nullptr ? chunk_valid_cols(n, p.N, p.slab_counts, p.slab_n0, p.slab_rows) : 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (w == 0.f) ? 0.f : w * ptx::ex2_approx(fmaf(v[j], k2, c2));
+    for (int j = 0; j < 32; ++j) v[j] = (w == 0.f || j >= lim) ? 0.f : w * ptx::ex2_approx(fmaf(v[j], k2, c2));
     const int rel = lab - n;
     if (rel >= 0 && rel < 32) {
 #pragma unroll
@@ -546,9 +582,11 @@ static size_t ce_carve(CeWorkspace* w, void* base, int M, int N, int D = 0) {
 }
 
 int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
-                const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* ws,
+                const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
   CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_fwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
+  CLIPK_REQUIRE(slab_counts == nullptr || (slab_rows > 0 && slab_rows % 32 == 0 && slab_n0 % 32 == 0),
+                "ce_feat: hard-negative slabs need slab_n0 (%d) and slab_rows (%d) to be multiples of 32", slab_n0, slab_rows);
   CeWorkspace w{};
   const size_t need = ce_carve(&w, ws, M, N);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "ce_feat_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -558,7 +596,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   const int ks[1] = {(D + 63) / 64};
   const int tiles_n = 2 * ((N + 255) / 256);   // one partial per (n-tile, epilogue-warp half)
   CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
-  epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias};
+  epi::LsePart::Params ep{w.part, w.pos, labels, label_offset, M, N, tiles_n, scale, bias, scale_dev, slab_counts, slab_n0, slab_rows};
   CLIPK_TRY((ce_launch<256, false, false, epi::LsePart>(ce_engine(M), &a, &b, ks, M, N, ep, st)));
   lse_merge_kernel<<<(M + 127) / 128, 128, 0, st>>>(w.part, w.pos, M, tiles_n, labels, label_offset, N, row_lse, row_loss);
   clipk::count_launches(1);
@@ -567,7 +605,7 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
 }
 
 int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
-                const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, void* dXv,
+                const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, void* dXv,
                 int accX, void* dYv, int accY, int grads_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
   CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_bwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
   // bf16 gradients: written straight from the GEMM epilogues (TMA stores) / the slab sum; needs a single row chunk
@@ -592,11 +630,11 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
       if (ce_engine(mc) == 2 && ce_dl_tma()) {
         epi::DlOutTma::Params ep{{w.dL, ldd, (int64_t)mc * ldd, mc, N, 1}, row_lse + m0, row_w + m0,
-                                 labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0), mc, N, scale, bias};
+                                 labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0), mc, N, scale, bias, scale_dev, slab_counts, slab_n0, slab_rows};
         CLIPK_TRY((launch_gemm2<256, false, false, epi::DlOutTma>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st)));
       } else {
         epi::DlOut::Params ep{row_lse + m0, row_w + m0, labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0),
-                              w.dL, ldd, mc, N, scale, bias};
+                              w.dL, ldd, mc, N, scale, bias, scale_dev, slab_counts, slab_n0, slab_rows};
         CLIPK_TRY((ce_launch<256, false, false, epi::DlOut>(ce_engine(mc), &a, &b, ksD, mc, N, ep, st)));
       }
     }
@@ -612,7 +650,7 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
         a.ptr = w.dL; a.rows = mc; a.k = N; a.ld = ldd; a.k_batch_offset = sp.ksplit;
         b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
         const int ks[1] = {(sp.ksplit + 63) / 64};
-        epi::Store<false>::Params ep{w.slabs, D, (int64_t)mc * D, mc, D, scale, 0};
+        epi::Store<false>::Params ep{w.slabs, D, (int64_t)mc * D, mc, D, scale, 0, scale_dev};
         CLIPK_TRY((launch_gemm2<256, false, true, epi::Store<false>>(&a, &b, 1, ks, ks, mc, D, nfull, ep, st)));
       }
       const int64_t n4 = (int64_t)mc * D / 4;
@@ -630,10 +668,10 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = Y; b.mn_major = true; b.rows = D; b.k = N; b.ld = D;
       const int ks[1] = {(N + 63) / 64};
       if (grads_bf16) {
-        epi::StoreTma::Params ep{{dXv, D, (int64_t)mc * D, mc, D, 1}, scale};
+        epi::StoreTma::Params ep{{dXv, D, (int64_t)mc * D, mc, D, 1}, scale, scale_dev};
         CLIPK_TRY((launch_gemm2<256, false, true, epi::StoreTma>(&a, &b, 1, ks, ks, mc, D, 1, ep, st)));
       } else {
-        epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX};
+        epi::Store<false>::Params ep{dX + (int64_t)m0 * D, D, 0, mc, D, scale, accX, scale_dev};
         CLIPK_TRY((ce_launch<256, false, true, epi::Store<false>>(ce_engine(mc), &a, &b, ks, mc, D, ep, st)));
       }
     }
@@ -644,10 +682,10 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       b.ptr = X + (int64_t)m0 * D; b.mn_major = true; b.rows = D; b.k = mc; b.ld = D;
       const int ks[1] = {(mc + 63) / 64};
       if (grads_bf16) {
-        epi::StoreTma::Params ep{{dYv, D, (int64_t)N * D, N, D, 1}, scale};
+        epi::StoreTma::Params ep{{dYv, D, (int64_t)N * D, N, D, 1}, scale, scale_dev};
         CLIPK_TRY((launch_gemm2<256, true, true, epi::StoreTma>(&a, &b, 1, ks, ks, N, D, 1, ep, st)));
       } else {
-        epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0};
+        epi::Store<false>::Params ep{dY, D, 0, N, D, scale, (accY || m0 > 0) ? 1 : 0, scale_dev};
         CLIPK_TRY((ce_launch<256, true, true, epi::Store<false>>(ce_engine(N), &a, &b, ks, N, D, ep, st)));
       }
     }
@@ -754,29 +792,32 @@ size_t clipk_ce_feat_bwd_workspace_bytes(int M, int N, int D) {
 }
 
 int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+        const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows,
                       const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
                       size_t ws_bytes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::ce_feat_fwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
-                            bias, labels, label_offset, row_lse, row_loss, workspace, ws_bytes,
+                            bias, scale_dev, slab_counts, slab_n0, slab_rows, labels, label_offset, row_lse, row_loss, workspace, ws_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 
 int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+        const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows,
                       const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
-                            bias, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, 0, workspace, ws_bytes,
+                            bias, scale_dev, slab_counts, slab_n0, slab_rows, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, 0, workspace, ws_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 
 int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+        const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows,
                            const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w,
                            void* dX, void* dY, void* workspace, size_t ws_bytes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
-                            bias, labels, label_offset, row_lse, row_w, dX, 0, dY, 0, 1, workspace, ws_bytes,
+                            bias, scale_dev, slab_counts, slab_n0, slab_rows, labels, label_offset, row_lse, row_w, dX, 0, dY, 0, 1, workspace, ws_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 }

@@ -70,9 +70,12 @@ struct Store {
     int M, N;
     float alpha;
     int accumulate;
+    const float* alpha_dev;   // nullable: alpha read from device memory (no host copy of a device scalar)
   };
   Params p;
-  __device__ explicit Store(const Params& pp) : p(pp) {}
+  __device__ explicit Store(const Params& pp) : p(pp) {
+    if (p.alpha_dev != nullptr) p.alpha = __ldg(p.alpha_dev);
+  }
   __device__ void tile_begin(int, int, int) {}
   __device__ void chunk(int b, int m, int n, float* v) {
     if (m >= p.M || n >= p.N) return;
@@ -188,9 +191,12 @@ struct StoreTma {
   struct Params {
     eng::OutDesc out;
     float alpha;
+    const float* alpha_dev;   // nullable
   };
   Params p;
-  __device__ explicit StoreTma(const Params& pp) : p(pp) {}
+  __device__ explicit StoreTma(const Params& pp) : p(pp) {
+    if (p.alpha_dev != nullptr) p.alpha = __ldg(p.alpha_dev);
+  }
   __device__ void tile_begin(int, int, int) {}
   __device__ void chunk(int, int, int, float* v) {
 #pragma unroll

@@ -87,9 +87,13 @@ def _splice_local(all_x, local_x, rank_):
 
 
 def gather_features(image_features, text_features, b, usehardtext, gather_with_grad, local_loss, rank_, world,
-                    group=None):
+                    group=None, keep_padding=False):
     """(all_image [N,D], all_text [N + sum_r H_r, D]); text rows ordered [orig_0 .. orig_{W-1}, hard_0 .. hard_{W-1}]
-    exactly as loss.py:147-153 re-orders them."""
+    exactly as loss.py:147-153 re-orders them.
+
+    keep_padding=True (usehardtext only) returns (all_image, all_text [2N, D], counts int32 [W]) instead: the hard
+    negatives of rank r occupy rows [N + r b, N + r b + counts[r]) and the rest of each b-row slab is zero padding that
+    the CE kernels mask out -- nothing about the ragged sizes ever reaches the host."""
     gather = all_gather_with_grad if gather_with_grad else all_gather_nograd
     all_img = gather(image_features, group)
     if not usehardtext:
@@ -107,9 +111,14 @@ def gather_features(image_features, text_features, b, usehardtext, gather_with_g
     padded = text_features
     if h < b:
         padded = torch.cat([text_features, text_features.new_zeros((b - h, D))], dim=0)
-    counts = all_gather_nograd(torch.tensor([h], dtype=torch.int64, device=text_features.device), group)
+    counts = all_gather_nograd(torch.tensor([h], dtype=torch.int32, device=text_features.device), group)
     slabs = gather(padded, group).reshape(world, 2 * b, D)
-    hs = counts.tolist()                     # the only host sync: sizes of the ragged tail
+    if keep_padding:
+        # no host sync, no ragged cat: [orig_0 .. orig_{W-1} | slab_0 .. slab_{W-1}] with every hard-negative slab at its
+        # full capacity of b rows; the consumer masks rows >= counts[r] of slab r on the device (feat_row_ce `slab`)
+        all_txt = torch.cat([slabs[:, :b].reshape(world * b, D), slabs[:, b:].reshape(world * b, D)], dim=0)
+        return all_img, all_txt, counts
+    hs = counts.tolist()                     # legacy compact layout: one host read of the ragged tail's sizes
     orig = slabs[:, :b].reshape(world * b, D)
     hard = [slabs[r, b:b + hs[r]] for r in range(world)]
     return all_img, torch.cat([orig] + hard, dim=0)

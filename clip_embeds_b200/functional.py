@@ -397,16 +397,28 @@ def symmetric_infonce(X, Y, scale):
 class _FeatRowCE(torch.autograd.Function):
     """sum over valid rows of CE(scale * X Y^T + bias, labels) and the number of valid rows.
 
-    bf16 inputs run on the tcgen05 engine (logits never materialised); fp32 inputs run the fp32 SIMT path."""
+    bf16 inputs run on the tcgen05 engine (logits never materialised); fp32 inputs run the fp32 path (one logits GEMM at
+    fp32 accuracy + row CE).  `scale` may be a python number or a device scalar tensor (open_clip hands over
+    `logit_scale.exp()` as a CUDA tensor, open_clip_train/train.py:107): a tensor is read by the kernels from device
+    memory -- no host copy, hence no stream stall -- and receives its gradient.  A constant `bias` added to every logit of
+    a row has zero gradient under cross-entropy (softmax sums to one), which is what is returned for a tensor bias."""
 
     @staticmethod
-    def forward(ctx, X, Y, scale, bias, labels, label_offset):
+    def forward(ctx, X, Y, scale, bias, labels, label_offset, slab):
         _need_cuda(X, Y)
         M, D = X.shape
         N = Y.shape[0]
         dev = X.device
         st = _stream()
         row_lse, row_loss = _f32(M, device=dev), _f32(M, device=dev)
+        # hard-negative slabs of Y (see clipk.h): (int32 fill counts [W] on the device, first slab column, rows per slab)
+        if slab is not None:
+            slab_counts, slab_n0, slab_rows = slab
+            slab_counts = slab_counts.to(device=dev, dtype=torch.int32).contiguous()
+            if slab_n0 % 32 or slab_rows % 32 or slab_n0 + slab_counts.numel() * slab_rows != N:
+                raise ValueError("slabs: slab_n0 and slab_rows must be multiples of 32 and cover Y's tail exactly")
+        else:
+            slab_counts, slab_n0, slab_rows = None, 0, 0
         lab_ptr = 0
         if labels is not None:
             labels = labels.to(device=dev, dtype=torch.int64).contiguous()
@@ -415,57 +427,86 @@ class _FeatRowCE(torch.autograd.Function):
         else:
             valid = torch.ones(M, dtype=torch.bool, device=dev)
         ctx.scale_needs_grad = torch.is_tensor(scale) and scale.requires_grad
-        sc = float(scale)        # NOTE: a device scalar costs one host sync here
-        bi = float(bias) if bias is not None else 0.0
+        ctx.bias_is_tensor = torch.is_tensor(bias)
+        scale_dev = None
+        if torch.is_tensor(scale) and scale.is_cuda:
+            scale_dev = scale.detach().to(torch.float32).reshape(1).contiguous()      # stays on the device
+            sc = 1.0
+        else:
+            sc = float(scale)
+        if torch.is_tensor(bias) and bias.is_cuda and bias.numel() == 1 and bias.requires_grad:
+            bi = float(bias.detach())      # (rare: a learnable bias; its value is needed on the host by the fp32 GEMM call)
+        else:
+            bi = float(bias) if bias is not None else 0.0
         if X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16:
             Xc, Yc = X.contiguous(), Y.contiguous()
             nbytes = _lib.lib().clipk_ce_feat_bwd_workspace_bytes(M, N, D)     # shared by forward and backward
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            _lib.call("clipk_ce_feat_fwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
-                      row_lse.data_ptr(), row_loss.data_ptr(), ws.data_ptr(), nbytes, st)
+            _lib.call("clipk_ce_feat_fwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, _p(scale_dev), _p(slab_counts),
+                      slab_n0, slab_rows, lab_ptr, label_offset, row_lse.data_ptr(), row_loss.data_ptr(), ws.data_ptr(),
+                      nbytes, st)
             ctx.ws = ws
             logits = None
         else:
             Xc, Yc = X.float().contiguous(), Y.float().contiguous()
             logits = _f32(M, N, device=dev)
-            if bi != 0.0:
-                logits.fill_(bi)
-            _gemm_f32(Xc, D, 1, Yc, 1, D, logits, N, M, N, D, sc, accumulate=bi != 0.0)
+            if scale_dev is None:
+                if bi != 0.0:
+                    logits.fill_(bi)
+                _gemm_f32(Xc, D, 1, Yc, 1, D, logits, N, M, N, D, sc, accumulate=bi != 0.0)
+            else:
+                _gemm_f32(Xc, D, 1, Yc, 1, D, logits, N, M, N, D, 1.0)
+                logits.mul_(scale_dev)
+                if bi != 0.0:
+                    logits.add_(bi)
+            if slab_counts is not None:        # mask the unfilled slab rows of Y out of the softmax (device-side mask)
+                col = torch.arange(N - slab_n0, device=dev)
+                dead = (col % slab_rows) >= slab_counts.to(torch.int64)[col // slab_rows]
+                logits[:, slab_n0:].masked_fill_(dead[None, :], float("-inf"))
             _lib.call("clipk_ce_rows", logits.data_ptr(), M, N, N, lab_ptr, label_offset, row_lse.data_ptr(),
                       row_loss.data_ptr(), st)
             ctx.ws = None
-        ctx.save_for_backward(Xc, Yc, row_lse, labels if labels is not None else torch.empty(0, device=dev), valid,
-                              logits if logits is not None else torch.empty(0, device=dev))
-        ctx.cfg = (sc, bi, labels is not None, label_offset, X.dtype, Y.dtype)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(Xc, Yc, row_lse, labels if labels is not None else empty, valid,
+                              logits if logits is not None else empty, scale_dev if scale_dev is not None else empty,
+                              slab_counts if slab_counts is not None else empty)
+        ctx.cfg = (sc, bi, labels is not None, label_offset, X.dtype, Y.dtype, scale_dev is not None,
+                   (slab_n0, slab_rows) if slab_counts is not None else None,
+                   scale.shape if torch.is_tensor(scale) else None)
         loss_sum = (row_loss * valid).sum()
         ctx.mark_non_differentiable(valid)
         return loss_sum, valid
 
     @staticmethod
     def backward(ctx, g_sum, _g_valid):
-        Xc, Yc, row_lse, labels, valid, logits = ctx.saved_tensors
-        sc, bi, has_labels, label_offset, xdt, ydt = ctx.cfg
+        Xc, Yc, row_lse, labels, valid, logits, scale_dev, slab_counts = ctx.saved_tensors
+        sc, bi, has_labels, label_offset, xdt, ydt, dev_scale, slab_geo, scale_shape = ctx.cfg
+        sl_ptr = slab_counts.data_ptr() if slab_geo is not None else 0
+        slab_n0, slab_rows = slab_geo if slab_geo is not None else (0, 0)
         M, D = Xc.shape
         N = Yc.shape[0]
         dev = Xc.device
         st = _stream()
         lab_ptr = labels.data_ptr() if has_labels else 0
+        sd_ptr = scale_dev.data_ptr() if dev_scale else 0
         row_w = (valid.float() * g_sum.float()).contiguous()
+        dbias = torch.zeros((), device=dev) if ctx.bias_is_tensor else None
         if (Xc.dtype == torch.bfloat16 and xdt == torch.bfloat16 and ydt == torch.bfloat16 and 128 < M <= 4096 and N > 128
                 and not ctx.scale_needs_grad):
             # bf16 gradients straight from the GEMM epilogues (no fp32 round trip + cast pass)
             dXb = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
             dYb = torch.empty(N, D, dtype=torch.bfloat16, device=dev)
             ws = ctx.ws
-            _lib.call("clipk_ce_feat_bwd_bf16", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
-                      row_lse.data_ptr(), row_w.data_ptr(), dXb.data_ptr(), dYb.data_ptr(), ws.data_ptr(), ws.numel(), st)
-            return dXb, dYb, None, None, None, None
+            _lib.call("clipk_ce_feat_bwd_bf16", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, sd_ptr, sl_ptr, slab_n0,
+                      slab_rows, lab_ptr, label_offset, row_lse.data_ptr(), row_w.data_ptr(), dXb.data_ptr(),
+                      dYb.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            return dXb, dYb, None, dbias, None, None, None
         dX, dY = _f32(M, D, device=dev), _f32(N, D, device=dev)
         if Xc.dtype == torch.bfloat16:
             ws = ctx.ws
-            _lib.call("clipk_ce_feat_bwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, lab_ptr, label_offset,
-                      row_lse.data_ptr(), row_w.data_ptr(), dX.data_ptr(), 0, dY.data_ptr(), 0, ws.data_ptr(),
-                      ws.numel(), st)
+            _lib.call("clipk_ce_feat_bwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, sd_ptr, sl_ptr, slab_n0,
+                      slab_rows, lab_ptr, label_offset, row_lse.data_ptr(), row_w.data_ptr(), dX.data_ptr(), 0,
+                      dY.data_ptr(), 0, ws.data_ptr(), ws.numel(), st)
         else:
             dL = torch.empty_like(logits)
             _lib.call("clipk_ce_rows_grad", logits.data_ptr(), M, N, N, row_lse.data_ptr(), lab_ptr, label_offset,
@@ -473,16 +514,21 @@ class _FeatRowCE(torch.autograd.Function):
             # dX = scale * dL Y ; dY = scale * dL^T X
             _gemm_f32(dL, N, 1, Yc, D, 1, dX, D, M, D, N, sc)
             _gemm_f32(dL, 1, N, Xc, D, 1, dY, D, N, D, M, sc)
+            if dev_scale:
+                dX.mul_(scale_dev)
+                dY.mul_(scale_dev)
         dscale = None
         if ctx.scale_needs_grad:      # d/dscale sum(dlogits * x.y) = <dX, X> / scale
-            dscale = (dX * Xc.float()).sum() / sc
-        return dX.to(xdt), dY.to(ydt), dscale, None, None, None
+            dscale = ((dX * Xc.float()).sum() / (scale_dev.reshape(()) if dev_scale else sc)).reshape(scale_shape)
+        return dX.to(xdt), dY.to(ydt), dscale, dbias, None, None, None
 
 
-def feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0):
+def feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0, slab=None):
     """Mean over non-ignored rows of cross_entropy(scale * X @ Y.T + bias, labels)  (F.cross_entropy semantics,
-    ignore_index = any negative label).  labels=None means label_i = i + label_offset."""
-    loss_sum, valid = _FeatRowCE.apply(X, Y, scale, bias, labels, int(label_offset))
+    ignore_index = any negative label).  labels=None means label_i = i + label_offset.
+    slab = (counts int32 [W], first slab column, rows per slab): Y's tail holds W fixed-capacity slabs of hard negatives,
+    the unfilled rows are masked out of the softmax on the device."""
+    loss_sum, valid = _FeatRowCE.apply(X, Y, scale, bias, labels, int(label_offset), slab)
     return loss_sum / valid.sum().clamp_min(1)
 
 

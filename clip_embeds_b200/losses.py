@@ -70,6 +70,20 @@ class OpenClipLoss(nn.Module):
         self.use_horovod = use_horovod
         self.usehardtext = usehardtext
         self.group = group
+        self._labels = {}
+
+    def _text_labels(self, text, n_orig, offset):
+        """labels of the text->image CE (loss.py:127-135): row i < n_orig -> i + offset, hard-negative (and padding) rows
+        -> ignore_index.  With cache_labels the tensor is built once per (rows, n_orig, offset, device), as the reference
+        caches its ground truth (loss.py:110-125)."""
+        key = (text.shape[0], n_orig, offset, text.device)
+        if self.cache_labels and key in self._labels:
+            return self._labels[key]
+        lab = torch.full((text.shape[0],), -100, dtype=torch.int64, device=text.device)
+        lab[:n_orig] = torch.arange(n_orig, device=text.device) + offset
+        if self.cache_labels:
+            self._labels[key] = lab
+        return lab
 
     def forward(self, image_features, text_features, logit_scale, logit_bias=None, output_dict=False):
         b = image_features.shape[0]
@@ -77,28 +91,30 @@ class OpenClipLoss(nn.Module):
         if self.world_size > 1:
             if self.usehardtext:
                 assert self.gather_with_grad, "usehardtext requires gather_with_grad (loss.py:77)"
-            all_img, all_txt = cdist.gather_features(image_features, text_features, b, self.usehardtext,
-                                                     self.gather_with_grad, self.local_loss, self.rank,
-                                                     self.world_size, self.group)
+            # device-side masks instead of the reference's size exchange (loss.py:78-86) whenever the slab geometry allows
+            # it (b a multiple of 32: the CE kernels mask whole 32-column chunks' tails)
+            fixed = self.usehardtext and b % 32 == 0 and image_features.is_cuda
+            if fixed:
+                all_img, all_txt, counts = cdist.gather_features(image_features, text_features, b, True,
+                                                                 self.gather_with_grad, self.local_loss, self.rank,
+                                                                 self.world_size, self.group, keep_padding=True)
+                slab = (counts, self.world_size * b, b)
+            else:
+                all_img, all_txt = cdist.gather_features(image_features, text_features, b, self.usehardtext,
+                                                         self.gather_with_grad, self.local_loss, self.rank,
+                                                         self.world_size, self.group)
+                slab = None
             if self.local_loss:
                 off = b * self.rank
-                li = Fk.feat_row_ce(image_features, all_txt, logit_scale, bias, None, off)
-                n_txt = text_features.shape[0]
-                lab_t = torch.full((n_txt,), -100, dtype=torch.int64, device=text_features.device)
-                lab_t[:b] = torch.arange(b, device=text_features.device) + off
-                lt = Fk.feat_row_ce(text_features, all_img, logit_scale, bias, lab_t, 0)
+                li = Fk.feat_row_ce(image_features, all_txt, logit_scale, bias, None, off, slab)
+                lt = Fk.feat_row_ce(text_features, all_img, logit_scale, bias, self._text_labels(text_features, b, off), 0)
             else:
                 N = all_img.shape[0]
-                li = Fk.feat_row_ce(all_img, all_txt, logit_scale, bias, None, 0)
-                lab_t = torch.full((all_txt.shape[0],), -100, dtype=torch.int64, device=all_txt.device)
-                lab_t[:N] = torch.arange(N, device=all_txt.device)
-                lt = Fk.feat_row_ce(all_txt, all_img, logit_scale, bias, lab_t, 0)
+                li = Fk.feat_row_ce(all_img, all_txt, logit_scale, bias, None, 0, slab)
+                lt = Fk.feat_row_ce(all_txt, all_img, logit_scale, bias, self._text_labels(all_txt, N, 0), 0)
         else:
             li = Fk.feat_row_ce(image_features, text_features, logit_scale, bias, None, 0)
-            n_txt = text_features.shape[0]
-            lab_t = torch.full((n_txt,), -100, dtype=torch.int64, device=text_features.device)
-            lab_t[:b] = torch.arange(b, device=text_features.device)
-            lt = Fk.feat_row_ce(text_features, image_features, logit_scale, bias, lab_t, 0)
+            lt = Fk.feat_row_ce(text_features, image_features, logit_scale, bias, self._text_labels(text_features, b, 0), 0)
         total = (li + lt) / 2
         return {"contrastive_loss": total} if output_dict else total
 

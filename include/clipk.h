@@ -147,16 +147,24 @@ size_t clipk_ce_feat_workspace_bytes(int M, int N);
 /* backward workspace including the split-K slabs of the dX GEMM (a workspace sized by the query above still works:
  * the dX GEMM then runs unsplit) */
 size_t clipk_ce_feat_bwd_workspace_bytes(int M, int N, int D);
-int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
-                      const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
+/* `scale_dev` (nullable): when given, the logit scale is read from this device scalar instead of `scale` -- open_clip
+ * passes logit_scale.exp() as a CUDA tensor (open_clip_train/train.py:107), and copying it to the host would stall the
+ * stream once per call.
+ * `slab_counts` (nullable, int32 [W] on the device) with `slab_n0`, `slab_rows`: the columns of Y from slab_n0 on are W
+ * fixed-capacity slabs of slab_rows rows (each rank's hard-negative captions, all-gathered at capacity); only the first
+ * slab_counts[r] rows of slab r exist, the rest are masked out of the softmax (the reference's host-side size exchange,
+ * loss.py:78-86, becomes an in-band device array).  slab_n0 and slab_rows must be multiples of 32. */
+int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                      const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, float* row_lse, float* row_loss, void* workspace,
                       size_t ws_bytes, void* stream);
-int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
-                      const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
+int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                      const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream);
 
 /* The same backward with bf16 gradients written straight from the GEMM epilogues (dX, dY bf16, both required, no
  * accumulation); supported for 128 < M <= 4096 and N > 128 (CLIPK_ERR_INVALID otherwise: use the fp32 entry). */
 int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, float scale, float bias,
+                           const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows,
                            const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w,
                            void* dX, void* dY, void* workspace, size_t ws_bytes, void* stream);
 

@@ -23,7 +23,8 @@ def _free_port():
     return p
 
 
-def _cpu_feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0):
+def _cpu_feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0, slab=None):
+    assert slab is None
     logits = float(scale) * X.float() @ Y.float().T + float(bias if bias is not None else 0.0)
     if labels is None:
         labels = torch.arange(X.shape[0]) + label_offset

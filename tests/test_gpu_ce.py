@@ -161,3 +161,44 @@ def test_pacl_cliploss_fp32(B):
     assert abs(loss.item() - lo.item()) < 1e-5 * abs(lo.item())
     assert rel_l2(img.grad.cpu(), io.grad) < 2e-5
     assert rel_l2(txt.grad.cpu(), to.grad) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_feat_row_ce_hard_negative_slabs(dtype):
+    """Fixed-capacity hard-negative slabs masked on the device (`slab`; reference: the host-side size exchange of
+    gather_features_diffsize, loss.py:78-86): CE over Y = [N originals | W slabs of b rows, counts[r] of them filled] equals
+    CE over the compact Y, and the padding rows receive exactly zero gradient -- with the logit scale as a device tensor."""
+    import clip_embeds_b200.functional as Fk
+    W, b, D, M = 3, 64, 256, 160
+    counts = [17, 0, 64]
+    N0 = W * b
+    g = torch.Generator().manual_seed(123)
+    X = O.l2n(torch.randn(M, D, generator=g)).to(dtype)
+    orig = O.l2n(torch.randn(N0, D, generator=g)).to(dtype)
+    hard = [O.l2n(torch.randn(c, D, generator=g)).to(dtype) for c in counts]
+    compact = torch.cat([orig] + hard, 0)
+    padded = torch.cat([orig] + [torch.cat([h, torch.zeros(b - h.shape[0], D, dtype=dtype)], 0) for h in hard], 0)
+    scale = torch.tensor(25.0, device="cuda")
+    res = []
+    for Y, slab in ((compact, None), (padded, (torch.tensor(counts, dtype=torch.int32, device="cuda"), N0, b))):
+        Xg = X.cuda().requires_grad_()
+        Yg = Y.cuda().requires_grad_()
+        loss = Fk.feat_row_ce(Xg, Yg, scale, 0.0, None, 5, slab)
+        loss.backward()
+        res.append((loss.item(), Xg.grad.float().cpu(), Yg.grad.float().cpu()))
+    (l0, dx0, dy0), (l1, dx1, dy1) = res
+    assert abs(l0 - l1) < 1e-4 * max(1.0, abs(l0))
+    assert rel_l2(dx1, dx0) < 2e-3
+    # gradient rows of the padded layout: filled rows match the compact layout, padding rows are exactly zero
+    off = N0
+    assert rel_l2(dy1[:N0], dy0[:N0]) < 2e-3
+    for r, c in enumerate(counts):
+        rows = dy1[N0 + r * b:N0 + (r + 1) * b]
+        if c:
+            assert rel_l2(rows[:c], dy0[off:off + c]) < 2e-3
+        assert float(rows[c:].abs().max()) == 0.0 if c < b else True
+        off += c
+    # oracle cross-check of the compact problem
+    Xo, Yo = X.float().requires_grad_(), compact.float().requires_grad_()
+    lo = torch.nn.functional.cross_entropy(25.0 * Xo @ Yo.T, torch.arange(M) + 5)
+    assert abs(l0 - lo.item()) < 2e-3 * max(1.0, abs(lo.item()))
