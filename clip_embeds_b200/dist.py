@@ -81,6 +81,23 @@ def all_reduce_sum_with_grad(x, group=None):
     return _AllReduceSumGrad.apply(x, group)
 
 
+class _ScaleGrad(torch.autograd.Function):
+    """Identity in the forward pass; multiplies the gradient by `factor` in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, factor):
+        ctx.factor = factor
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.factor, None
+
+
+def scale_grad(x, factor):
+    return _ScaleGrad.apply(x, float(factor))
+
+
 def _splice_local(all_x, local_x, rank_):
     n = local_x.shape[0]
     return torch.cat([all_x[: rank_ * n], local_x, all_x[(rank_ + 1) * n:]], dim=0)

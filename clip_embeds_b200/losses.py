@@ -25,18 +25,33 @@ class ClipLoss(nn.Module):
         return Fk.symmetric_infonce(image_features, text_features, self.logit_scale)
 
 
+GRAD_REDUCTIONS = ("sum", "mean")
+
+
 class PaclAllPairsLoss(nn.Module):
     """InfoNCE over the all-pairs text-conditioned score matrix; image-sharded across `group` ranks.
 
     forward(visual_proj [b,P,D] (this rank's images), text_proj [b,D] (this rank's captions)) -> global loss.
-    Texts are all-gathered (with gradient: reduce-scatter in backward), V never moves."""
+    Texts are all-gathered (with gradient: reduce-scatter in backward), V never moves.
 
-    def __init__(self, temperature=0.1, activation="sigmoid", group=None, image_group=None):
+    Gradient convention under sharding (`grad_reduction`): every rank returns the GLOBAL loss L and back-propagates
+    through its own rows only.
+      "sum"  (default): the inputs of rank r receive exactly dL/d(inputs of rank r).  Parameters shared by the ranks
+             (the projection heads) then need their gradients SUM-reduced across ranks.
+      "mean": the same gradients multiplied by the world size, so that a MEAN reduction -- what
+             torch.nn.parallel.DistributedDataParallel does -- yields dL/d(parameters).  This is the convention of the
+             reference's open_clip ClipLoss (every rank differentiates the full loss, the gather's backward sums) and of
+             VLM2Vec's loss (`* world_size`, VLM2Vec/src/loss.py:35-41); use it whenever the heads are wrapped in DDP."""
+
+    def __init__(self, temperature=0.1, activation="sigmoid", group=None, image_group=None, grad_reduction="sum"):
         super().__init__()
+        if grad_reduction not in GRAD_REDUCTIONS:
+            raise ValueError(f"grad_reduction must be one of {GRAD_REDUCTIONS}")
         self.logit_scale = 1.0 / temperature
         self.activation = activation
         self.group = group
         self.image_group = image_group
+        self.grad_reduction = grad_reduction
 
     def forward(self, visual_proj, text_proj):
         pg = self.group
@@ -48,7 +63,10 @@ class PaclAllPairsLoss(nn.Module):
             all_text = text_proj
             offset = 0
         scores = Fk.pacl_scores(visual_proj, all_text, self.logit_scale, self.activation, self.image_group)
-        return Fk.score_infonce(scores, offset, pg)
+        loss = Fk.score_infonce(scores, offset, pg)
+        if pg is not None and self.grad_reduction == "mean":
+            loss = cdist.scale_grad(loss, cdist.world_size(pg))
+        return loss
 
 
 class OpenClipLoss(nn.Module):
@@ -128,11 +146,14 @@ class SparcLoss(ClipLoss):
     DataParallel run does (outputs gathered before the loss, train_sparc.py:92-94); the returned value is the
     global loss, identical on every rank."""
 
-    def __init__(self, temperature, group=None):
+    def __init__(self, temperature, group=None, grad_reduction="sum"):
         super().__init__(temperature)
+        if grad_reduction not in GRAD_REDUCTIONS:
+            raise ValueError(f"grad_reduction must be one of {GRAD_REDUCTIONS}")
         self.global_weight = 0.5
         self.local_weight = 1.0
         self.group = group
+        self.grad_reduction = grad_reduction     # see PaclAllPairsLoss: "mean" when the heads are wrapped in DDP
 
     def forward(self, v_patch_embed, l_token_embed, l_grouped_v_patch_embed, language_mask):
         gi = Fk.normalize_rows(Fk.pooled_patch_mean(v_patch_embed))
@@ -152,7 +173,8 @@ class SparcLoss(ClipLoss):
             cdist.all_reduce_sum_(msum, pg)
             local_part = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale, msum)
             total = self.global_weight * global_part + self.local_weight * local_part
-            return cdist.all_reduce_sum_with_grad(total, pg)
+            total = cdist.all_reduce_sum_with_grad(total, pg)
+            return cdist.scale_grad(total, W) if self.grad_reduction == "mean" else total
         global_loss = Fk.symmetric_infonce(gi, gt, self.logit_scale)
         local_loss = Fk.sparc_local_loss(l_grouped_v_patch_embed, l_token_embed, language_mask, self.logit_scale)
         return self.global_weight * global_loss + self.local_weight * local_loss

@@ -91,6 +91,12 @@ def g2(pacl):
     # reference stub returns the full V regardless of input, mirror that for the check
     sg_ref_like = O.l2n(V2.detach().mean(1)) @ O.l2n(O.l2n(L2.detach()).mean(1)).T
     _close(sg_ref_like, out["scoring_global"], what="G2 scoring")
+    # local scoring (pacl.py:443-451, local=True): grouped patch embeddings against the token embeddings, both mean-pooled
+    # over all 77 positions; same stub behaviour (the reference saw the full V / L), so the oracle is evaluated on them
+    sl_ref_like = O.l2n(gh2.detach().mean(1)) @ O.l2n(lh2.detach().mean(1)).T
+    _close(sl_ref_like, out["scoring_local"], what="G2 scoring local")
+    sl_oracle = O.sparc_scoring(V2.detach(), L2.detach(), mask, 1.0 / P, local=True)
+    _close(sl_oracle, out["scoring_local"], what="G2 scoring local (oracle.sparc_scoring)")
     del sg
     return out
 

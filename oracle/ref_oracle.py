@@ -257,8 +257,8 @@ def whatsup_accounting(scores, set_id, rel_id):
     """eval_pacl.py:53-104 on precomputed diagonal scores [items,K]: `correct` is the strict comparison of caption 0
     against every other caption (:56, :133); eval_dict[(object pair)][relation] = correct (:59-60, later items
     overwrite); individual / pair / set counts (:63-85).  Returns (counts [ind_lr, ind_ou, ind_fb, pair_lr, pair_ou,
-    pair_fb, sets, total], correct list).  Parity: restated from the script (it needs the datasets and a model to
-    run), not pinned by a reference output."""
+    pair_fb, sets, total], correct list).  Parity: pinned by golden G11 -- the reference's own `eval` / `eval_4`
+    executed unmodified on planted scores (oracle/make_golden_protocols.py, tests/golden/goldens_protocols.json)."""
     items, K = scores.shape
     correct = [int(all(bool(scores[i, 0] > scores[i, k]) for k in range(1, K))) for i in range(items)]
     eval_dict = {}

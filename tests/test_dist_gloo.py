@@ -116,6 +116,20 @@ def _worker(rank, world, port, case, q):
             loss = losses.PaclAllPairsLoss(0.1, group=dist.group.WORLD)(Vl, Tl)
             loss.backward()
             q.put((rank, loss.item(), Vl.grad.tolist(), Tl.grad.tolist()))
+        elif case == "allpairs_ddp":
+            # a small shared head in front of the sharded loss, wrapped in DDP (mean-reduces parameter gradients):
+            # grad_reduction="mean" must give the head the gradient of the GLOBAL loss
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            Bi, P, D = 6, 20, 16
+            V = O.rn(91, Bi, P, D)
+            T = O.rn(92, Bi, D)
+            b = Bi // world
+            torch.manual_seed(5)
+            head = DDP(torch.nn.Linear(D, D, bias=False))
+            loss = losses.PaclAllPairsLoss(0.1, group=dist.group.WORLD, grad_reduction="mean")(
+                head(V[rank * b:(rank + 1) * b]), T[rank * b:(rank + 1) * b])
+            loss.backward()
+            q.put((rank, loss.item(), head.module.weight.grad.tolist(), []))
         elif case == "sparc":
             B, T_, P, D = 6, 9, 12, 16
             V, L = O.rn(93, B, P, D), O.rn(94, B, T_, D)
@@ -181,3 +195,19 @@ def test_sparc_sharded_two_ranks():
         assert abs(res[r][1] - lo.item()) < 1e-5
         assert torch.allclose(torch.tensor(res[r][2]), V.grad[r * 3:(r + 1) * 3], atol=1e-5)
         assert torch.allclose(torch.tensor(res[r][3]), L.grad[r * 3:(r + 1) * 3], atol=1e-5)
+
+
+def test_allpairs_ddp_mean_reduce_gives_global_gradient():
+    """under torch DDP (parameter gradients are MEAN-reduced) the sharded loss must hand every rank
+    world_size x its share, so that the head receives d(global loss)/d(weights) -- `grad_reduction="mean"`."""
+    res = _spawn("allpairs_ddp")
+    Bi, P, D = 6, 20, 16
+    V = O.rn(91, Bi, P, D)
+    T = O.rn(92, Bi, D)
+    torch.manual_seed(5)
+    head = torch.nn.Linear(D, D, bias=False)
+    lo = O.pacl_allpairs_loss(head(V), T, 0.1)
+    lo.backward()
+    for r in range(2):
+        assert abs(res[r][1] - lo.item()) < 1e-5
+        assert torch.allclose(torch.tensor(res[r][2]), head.weight.grad, atol=1e-5)

@@ -68,3 +68,24 @@ def test_mmvp_end_to_end_matches_oracle():
     got = evalproto.mmvp_accuracies(V1.cuda(), V2.cuda(), T.cuda(), gt, 15, 2)
     assert torch.equal(got["pred"].cpu(), pred)
     assert got["per_category_counts"] == want
+
+
+def test_protocols_match_reference_golden_g11():
+    """The CUDA protocol kernels against G11: the numbers the reference's own eval / eval_4 / eval_MMVP wrote (executed
+    unmodified on planted scores, oracle/make_golden_protocols.py), exact ties included."""
+    import json
+    import os
+    from clip_embeds_b200 import evalproto
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "goldens_protocols.json")))
+    for name in ("eval", "eval_4"):
+        c = G[name]
+        got = evalproto.whatsup_from_scores(torch.tensor(c["scores"]).cuda(), torch.tensor(c["set_id"]), torch.tensor(c["rel_id"]))
+        for k, v in c["reference"].items():
+            assert abs(got[k] - v) < 1e-9, (name, k, got[k], v)
+    for name in ("mmvp", "mmvpvlm"):
+        c = G[name]
+        got = evalproto.mmvp_from_scores(torch.tensor(c["s1"]).cuda(), torch.tensor(c["s2"]).cuda(), torch.tensor(c["gt"]),
+                                         c["pairs_per_cat"], c["ncat"])
+        assert got["pred"].cpu().tolist() == c["pred"]
+        assert abs(got["Pair"] - c["reference"]["Pair"]) < 1e-9
+        assert abs(got["Individual"] - c["reference"]["Individual"]) < 1e-9

@@ -115,3 +115,12 @@ def test_sparc_step_cuda_graph_replay_is_bit_identical():
     torch.cuda.synchronize()
     assert gs.loss.item() == ref
     assert torch.equal(V.grad, gV) and torch.equal(L.grad, gL)
+
+
+def test_c3_full_size_vs_oracle():
+    """BASELINE.json configs[2] AT ITS STATED SIZE: SPARC alignment + SparcLoss, B = 512, T = 77, P = 576, D = 768 (bf16
+    inputs), forward + backward against the fp32 oracle on the same bf16-rounded inputs (a few seconds of CPU)."""
+    g = torch.Generator().manual_seed(3)
+    eots = torch.randint(5, 77, (512,), generator=g).tolist()
+    e_g, e_l, dl, rv, rl = _run(512, 77, 576, 768, 301, eots)
+    assert e_g < 5e-3 and e_l < 1e-5 and dl < 5e-3 and rv < 4e-2 and rl < 4e-2

@@ -136,3 +136,36 @@ def test_g9_g10_metrics_and_vlm2vec_loss():
     loss.backward()
     assert abs(loss.item() - G["G10"]["loss"].item()) < 1e-5
     assert rel_l2(x.grad, G["G10"]["dx"]) < 1e-5 and rel_l2(y.grad, G["G10"]["dy"]) < 1e-5
+
+
+def test_g2_sparc_scoring_local_and_global(goldens):
+    """sparc.scoring (pacl.py:438-451), both modes, against the reference outputs stored with G2 (the generator's encoder
+    stubs return the full V / L, so the oracle is evaluated on the same tensors)."""
+    G = goldens["G2"]
+    B, T_, P, D = 4, 77, 196, 512
+    V, L = O.rn(3, B, P, D), O.rn(4, B, T_, D)
+    mask = (torch.arange(T_).expand(B, -1) <= G["eot"].unsqueeze(1)).float()
+    assert torch.allclose(O.sparc_scoring(V, L, mask, 1.0 / P, local=True), G["scoring_local"], atol=2e-6)
+    assert torch.allclose(O.sparc_scoring(V, L, mask, 1.0 / P, local=False), G["scoring_global"], atol=2e-6)
+
+
+def test_softmax_activation_independent_fp64_definition():
+    """north_star (2) 'softmax over the patches': no reference implementation exists, so the oracle's softmax
+    branch is checked against an INDEPENDENT fp64 statement of the definition written from Appendix A.1 alone --
+    a_p = softmax_p(10 cos(t, v_p)) with its true denominator, u = sum_p a_p V_p, features = n(u), n(t) -- including the
+    gradients (autograd through the fp64 definition)."""
+    V = O.rn(61, 5, 37, 24).double().requires_grad_()
+    T = O.rn(62, 5, 24).double().requires_grad_()
+    vh = V / V.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    th = T / T.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    s = torch.einsum("bd,bpd->bp", th, vh)
+    a = torch.exp(10.0 * s) / torch.exp(10.0 * s).sum(dim=-1, keepdim=True)          # plain softmax, written out
+    u = (a.unsqueeze(-1) * V).sum(dim=1)
+    img = u / u.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    w = O.rn(63, 5, 24).double()
+    ((img * w).sum() + (th * w).sum()).backward()
+    Vo, To = V.detach().float().requires_grad_(), T.detach().float().requires_grad_()
+    io, to = O.pacl_forward(Vo, To, "softmax")
+    ((io * w.float()).sum() + (to * w.float()).sum()).backward()
+    assert torch.allclose(io.double(), img.detach(), atol=2e-6) and torch.allclose(to.double(), th.detach(), atol=2e-6)
+    assert rel_l2(Vo.grad, V.grad) < 1e-5 and rel_l2(To.grad, T.grad) < 1e-5

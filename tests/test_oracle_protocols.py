@@ -48,3 +48,26 @@ def test_simple_contrastive_loss_label_map():
     y = O.l2n(O.rn(2, 12, 8))                              # 3 candidates per query: targets 0, 3, 6, 9
     want = torch.nn.functional.cross_entropy(x @ y.t() / 0.02, torch.tensor([0, 3, 6, 9]))
     assert torch.allclose(O.simple_contrastive_loss(x, y, 0.02), want)
+
+
+def test_protocol_accounting_matches_reference_golden_g11():
+    """G11 (tests/golden/goldens_protocols.json): what the reference's own `eval`, `eval_4` and `eval_MMVP`
+    (PACL/eval_pacl.py:26-104, :106-186, :236-349) wrote to evaluation_results.txt when executed UNMODIFIED on planted
+    scores (oracle/make_golden_protocols.py).  The oracle's restatements must reproduce every number."""
+    import json
+    import os
+    from oracle import make_golden_protocols as mg
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "goldens_protocols.json")))
+    mg.check_oracle(G)
+    # per-category MMVP numbers too (eval_pacl.py:341-349)
+    c = G["mmvpvlm"]
+    counts, _ = O.mmvp_accounting(torch.tensor(c["s1"]), torch.tensor(c["s2"]), torch.tensor(c["gt"]), 15, 9)
+    cats = ['Orientation and Direction', 'Presence of Specific Features', 'State and Condition', 'Quantity and Count',
+            'Positional and Relational Context', 'Color and Appearance', 'Structural Characteristics', 'Texts',
+            'Viewpoint and Perspective']
+    pairs = len(c["s1"])
+    for i, name in enumerate(cats):
+        assert abs(counts[i][0] / (pairs // 9) * 100 - c["reference"][f"{name} Pair accuracy"]) < 1e-9
+        assert abs(counts[i][1] / (pairs * 2 // 9) * 100 - c["reference"][f"{name} Single accuracy"]) < 1e-9
+    # the planted exact ties are in the data (strict comparison -> counted wrong)
+    assert any(s[0] == s[1] for s in G["eval"]["scores"])
