@@ -65,7 +65,7 @@ class SimpleContrastiveLoss:
         if target is None:
             tpq = y.size(0) // x.size(0)
             target = torch.arange(0, x.size(0) * tpq, tpq, device=x.device, dtype=torch.long)
-        loss_sum, valid = Fk._FeatRowCE.apply(x, y, 1.0 / self.temperature, 0.0, target, 0)
+        loss_sum, valid = Fk._FeatRowCE.apply(x, y, 1.0 / self.temperature, 0.0, target, 0, None)
         if reduction == "sum":
             return loss_sum
         if reduction != "mean":
