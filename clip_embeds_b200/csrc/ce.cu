@@ -453,6 +453,148 @@ struct DlOutTma {
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
+// ---------------------------------------------------------------------------------------- symmetric CE, one GEMM
+// Row AND column cross-entropy from ONE logits GEMM (open_clip computes `logits_per_text` with a second GEMM,
+// loss.py:156-157): besides the row partials of LsePart, every chunk adds its column sums
+//     col_sum[j] += sum_i exp(l_ij - ref),   ref = scale / 2 + bias      (columns j < ncol: the original captions)
+// with a FIXED reference instead of a running column maximum, so that partial sums -- of other row tiles and of other
+// ranks -- combine by plain addition (one atomicAdd per column and warp, one all-reduce across ranks).  Unit-norm
+// features bound the logits to [bias - scale, bias + scale]: l - ref <= scale / 2 <= 50 (open_clip clamps logit_scale
+// at 100) cannot overflow, and a column underflows only if its largest cosine is below 1/2 - 87 / scale (-0.37 at
+// scale 100) -- the column's own positive pair rules that out; col_lse[j] = ref + log(col_sum[j]).
+struct LseRowCol {
+  struct Params {
+    float2* part;            // [tiles_n][M] (max, sumexp) row partials, as LsePart
+    float* pos;              // [M] logit at the label column
+    int64_t label_offset;    // label of row m = m + label_offset
+    int M, N, tiles_n;
+    float scale, bias;
+    const float* scale_dev;  // nullable
+    const int* slab_counts;  // hard-negative slabs, see LsePart
+    int slab_n0, slab_rows;
+    float* col_sum;          // [ncol], zeroed by the caller
+    int ncol;
+  };
+  Params p;
+  float mx, sm, ref;
+  int64_t lab;
+  __device__ explicit LseRowCol(const Params& pp) : p(pp), mx(0.f), sm(0.f), lab(-1) {
+    if (p.scale_dev != nullptr) p.scale = __ldg(p.scale_dev);
+    ref = fmaf(0.5f, p.scale, p.bias);
+  }
+  __device__ void tile_begin(int, int m, int) {
+    mx = -INFINITY;
+    sm = 0.f;
+    lab = m < p.M ? (int64_t)m + p.label_offset : -1;
+  }
+  __device__ void chunk(int, int m, int n, float* v) {
+    if (n >= p.N) return;                                        // (warp-uniform)
+    const int lim = chunk_valid_cols(n, p.N, p.slab_counts, p.slab_n0, p.slab_rows);
+    if (lim <= 0) return;
+    const bool rowok = m < p.M;
+    float cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = fmaf(v[j], p.scale, p.bias);
+      if (j < lim) cm = fmaxf(cm, v[j]);
+    }
+    if (rowok) {
+      const float nm = fmaxf(mx, cm);
+      float acc = sm * __expf(mx - nm);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < lim) acc += __expf(v[j] - nm);
+      sm = acc;
+      mx = nm;
+      if (lab >= n && lab < (int64_t)n + 32 && lab < p.N) {
+        float pv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((int64_t)(n + j) == lab) pv = v[j];
+        p.pos[m] = pv;
+      }
+    }
+    if (n < p.ncol) {                                            // column sums over this warp's 32 rows
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e[j] = rowok ? __expf(v[j] - ref) : 0.f;
+      const float cs = ptx::warp_colsum32(e);                    // lane j: sum over the rows of column n + j
+      const int col = n + (int)ptx::lane_id();
+      if (col < p.ncol && cs != 0.f) atomicAdd(p.col_sum + col, cs);
+    }
+  }
+  __device__ void tile_end(int, int m, int, int tn, int half) {
+    if (m < p.M) p.part[(int64_t)(2 * tn + half) * p.M + m] = make_float2(mx, sm);
+  }
+};
+
+// dL[m][n] = w_m (exp(l - rlse_m) - [n == lab_m]) + (exp(l + cb_n) - cw_lab [n == lab_m])   as bf16 through TMA stores;
+// cb_n = log(col_w_n) - col_lse_n for the columns that carry a column CE (n < ncol), -inf elsewhere (Side: lane l holds
+// cb of column n + l, loaded one chunk ahead).
+struct DlSymTma {
+  static constexpr bool kTmaOut = true;
+  using Side = float;
+  struct Params {
+    eng::OutDesc out;        // dL [M][ldd] bf16, extents (M, N)
+    const float* lse;        // [M] row lse
+    const float* w;          // [M] row weights
+    int64_t label_offset;
+    int M, N;
+    float scale, bias;
+    const float* scale_dev;  // nullable
+    const int* slab_counts;
+    int slab_n0, slab_rows;
+    const float* col_bias;   // [ncol]
+    const float* col_w;      // [ncol]
+    int ncol;
+  };
+  Params p;
+  float nlse, w, wdiag;
+  int lab;
+  __device__ explicit DlSymTma(const Params& pp) : p(pp), nlse(0.f), w(0.f), wdiag(0.f), lab(-1) {
+    if (p.scale_dev != nullptr) p.scale = __ldg(p.scale_dev);
+  }
+  __device__ void tile_begin(int, int m, int) {
+    w = 0.f;
+    nlse = 0.f;
+    wdiag = 0.f;
+    lab = -1;
+    if (m < p.M) {
+      nlse = p.bias - p.lse[m];
+      w = p.w[m];
+      const int64_t l = (int64_t)m + p.label_offset;
+      lab = (l >= 0 && l < p.N) ? (int)l : -1;
+      wdiag = w + ((lab >= 0 && lab < p.ncol) ? __ldg(p.col_w + lab) : 0.f);
+    }
+  }
+  __device__ Side pre(int, int, int n) const {
+    const int col = n + (int)ptx::lane_id();
+    return col < p.ncol ? __ldg(p.col_bias + col) : -INFINITY;
+  }
+  __device__ void chunk(int, int m, int n, float* v, const Side& cb_l) {
+    const float L2E = 1.4426950408889634f;
+    const float k2 = p.scale * L2E, c2 = nlse * L2E, b2 = p.bias * L2E;
+    const int lim = p.slab_counts != nullptr ? chunk_valid_cols(n, p.N, p.slab_counts, p.slab_n0, p.slab_rows) : 32;
+    const bool rowok = m < p.M;
+    const float cbl2 = cb_l * L2E + b2;                       // -inf stays -inf
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float cj = __shfl_sync(0xffffffffu, cbl2, j);
+      const float x = v[j] * k2;
+      const float r = w * ptx::ex2_approx(x + c2);
+      const float c = ptx::ex2_approx(x + cj);                // 0 where the column carries no CE
+      v[j] = (rowok && j < lim) ? r + c : 0.f;
+    }
+    const int rel = lab - n;
+    if (rel >= 0 && rel < 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j == rel) v[j] -= wdiag;
+    }
+  }
+  __device__ void tile_end(int, int, int, int, int) {}
+};
+
 }  // namespace epi
 
 namespace clipk {
@@ -604,9 +746,44 @@ int ce_feat_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
   return 0;
 }
 
+// Symmetric CE forward: row lse / loss as ce_feat_fwd (labels = m + label_offset) plus the column sums of the first
+// `ncol` columns (col_sum, zeroed here).  CTA-pair engine only.
+int ce_sym_fwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
+               const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset,
+               int ncol, float* row_lse, float* row_loss, float* col_sum, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_sym_fwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
+  CLIPK_REQUIRE(ncol >= 0 && ncol <= N, "ce_sym_fwd: ncol=%d out of range (N=%d)", ncol, N);
+  CLIPK_REQUIRE(slab_counts == nullptr || (slab_rows > 0 && slab_rows % 32 == 0 && slab_n0 % 32 == 0),
+                "ce_sym: hard-negative slabs need slab_n0 (%d) and slab_rows (%d) to be multiples of 32", slab_n0, slab_rows);
+  CeWorkspace w{};
+  const size_t need = ce_carve(&w, ws, M, N);
+  CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "ce_sym_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  OperandDesc a, b;
+  a.ptr = X; a.rows = M; a.k = D; a.ld = D;
+  b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
+  const int ks[1] = {(D + 63) / 64};
+  const int tiles_n = 2 * ((N + 255) / 256);
+  CLIPK_CHECK_CUDA(cudaMemsetAsync(w.pos, 0, (size_t)M * 4, st));
+  if (ncol > 0) CLIPK_CHECK_CUDA(cudaMemsetAsync(col_sum, 0, (size_t)ncol * 4, st));
+  epi::LseRowCol::Params ep{w.part, w.pos, label_offset, M, N, tiles_n, scale, bias, scale_dev, slab_counts, slab_n0,
+                            slab_rows, col_sum, ncol};
+  CLIPK_TRY((launch_gemm2<256, false, false, epi::LseRowCol>(&a, &b, 1, ks, ks, M, N, 1, ep, st)));
+  lse_merge_kernel<<<(M + 127) / 128, 128, 0, st>>>(w.part, w.pos, M, tiles_n, nullptr, label_offset, N, row_lse, row_loss);
+  clipk::count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+struct CeSymBwd {           // column part of the symmetric backward (null col_bias: plain row CE)
+  const float* col_bias = nullptr;
+  const float* col_w = nullptr;
+  int ncol = 0;
+};
+
 int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
                 const float* scale_dev, const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, void* dXv,
-                int accX, void* dYv, int accY, int grads_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
+                int accX, void* dYv, int accY, int grads_bf16, void* ws, size_t ws_bytes, cudaStream_t st,
+                const CeSymBwd& sym = CeSymBwd()) {
   CLIPK_REQUIRE(M > 0 && N > 0 && D > 0 && D % 8 == 0, "ce_feat_bwd: bad shape M=%d N=%d D=%d (D %% 8 == 0)", M, N, D);
   // bf16 gradients: written straight from the GEMM epilogues (TMA stores) / the slab sum; needs a single row chunk
   // (dY is not accumulated across chunks) and the CTA-pair engine
@@ -628,7 +805,11 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       OperandDesc a, b;
       a.ptr = X + (int64_t)m0 * D; a.rows = mc; a.k = D; a.ld = D;
       b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
-      if (ce_engine(mc) == 2 && ce_dl_tma()) {
+      if (sym.col_bias != nullptr) {
+        epi::DlSymTma::Params ep{{w.dL, ldd, (int64_t)mc * ldd, mc, N, 1}, row_lse + m0, row_w + m0, label_offset + m0, mc, N,
+                                 scale, bias, scale_dev, slab_counts, slab_n0, slab_rows, sym.col_bias, sym.col_w, sym.ncol};
+        CLIPK_TRY((launch_gemm2<256, false, false, epi::DlSymTma>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st)));
+      } else if (ce_engine(mc) == 2 && ce_dl_tma()) {
         epi::DlOutTma::Params ep{{w.dL, ldd, (int64_t)mc * ldd, mc, N, 1}, row_lse + m0, row_w + m0,
                                  labels ? labels + m0 : nullptr, label_offset + (labels ? 0 : m0), mc, N, scale, bias, scale_dev, slab_counts, slab_n0, slab_rows};
         CLIPK_TRY((launch_gemm2<256, false, false, epi::DlOutTma>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st)));
@@ -809,6 +990,30 @@ int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float s
   return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
                             bias, scale_dev, slab_counts, slab_n0, slab_rows, labels, label_offset, row_lse, row_w, dX, accX, dY, accY, 0, workspace, ws_bytes,
                             static_cast<cudaStream_t>(stream));
+}
+
+int clipk_ce_sym_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                     const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol, float* row_lse,
+                     float* row_loss, float* col_sum, void* workspace, size_t ws_bytes, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  return clipk::ce_sym_fwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale, bias,
+                           scale_dev, slab_counts, slab_n0, slab_rows, label_offset, ncol, row_lse, row_loss, col_sum,
+                           workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int clipk_ce_sym_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                     const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol,
+                     const float* row_lse, const float* row_w, const float* col_bias, const float* col_w, void* dX,
+                     void* dY, int grads_bf16, void* workspace, size_t ws_bytes, void* stream) {
+  CLIPK_TRY(clipk::check_device());
+  CLIPK_REQUIRE(col_bias != nullptr && col_w != nullptr && ncol > 0 && ncol <= N, "ce_sym_bwd: column terms missing");
+  clipk::CeSymBwd sym;
+  sym.col_bias = col_bias;
+  sym.col_w = col_w;
+  sym.ncol = ncol;
+  return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
+                            bias, scale_dev, slab_counts, slab_n0, slab_rows, nullptr, label_offset, row_lse, row_w, dX, 0,
+                            dY, 0, grads_bf16, workspace, ws_bytes, static_cast<cudaStream_t>(stream), sym);
 }
 
 int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, float scale, float bias,

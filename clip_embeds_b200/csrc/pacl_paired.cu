@@ -126,7 +126,7 @@ pacl_paired_fwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
 }
 
 template <class T, int NIT>
-__global__ void __launch_bounds__(kPairedThreads)
+__global__ void __launch_bounds__(kPairedThreads, NIT <= 3 ? 2 : 1)
 pacl_paired_bwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B, int P, int D, int act,
                        const float* __restrict__ img_feat, const float* __restrict__ stats,
                        const float* __restrict__ d_img, const float* __restrict__ d_txt, T* __restrict__ dV,
@@ -171,18 +171,23 @@ pacl_paired_bwd_kernel(const T* __restrict__ V, const T* __restrict__ Tx, int B,
 
   const T* Vb = V + (int64_t)b * P * D;
   T* dVb = dV + (int64_t)b * P * D;
-  for (int p = warp; p < P; p += kPairedWarps) {
-    float v[NIT][8];
+  // two rows per warp in flight: the next row's loads are issued (raw, unconverted) before this row is processed --
+  // the occupancy is register-bound (2 CTAs / SM), so the bytes in flight per warp set the achieved bandwidth
+  simt::Raw8<T> nxt[NIT];
+  auto issue = [&](int p) {
     const T* row = Vb + (int64_t)p * D;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int d0 = it * 256 + lane * 8;
-      if (d0 < D) simt::load8<T>(row + d0, v[it]);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[it][j] = 0.f;
-      }
+      nxt[it] = (d0 < D && p < P) ? simt::load_raw8<T>(row + d0) : simt::zero_raw8<T>();
     }
+  };
+  issue(warp);
+  for (int p = warp; p < P; p += kPairedWarps) {
+    float v[NIT][8];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) simt::unpack_raw8(nxt[it], v[it]);
+    issue(p + kPairedWarps);
     float r = 0.f, nsq = 0.f, da = 0.f;
 #pragma unroll
     for (int it = 0; it < NIT; ++it)
@@ -312,6 +317,8 @@ int clipk_pacl_paired_fwd(const void* V, const void* T, int dtype, int B, int v_
     return clipk::paired_fwd_t<__nv_bfloat16>(V, T, B, v_div, P, D, act, act_out, img_feat, txt_feat, cosine, stats, st);
   if (dtype == CLIPK_F32)
     return clipk::paired_fwd_t<float>(V, T, B, v_div, P, D, act, act_out, img_feat, txt_feat, cosine, stats, st);
+  if (dtype == CLIPK_F16)
+    return clipk::paired_fwd_t<__half>(V, T, B, v_div, P, D, act, act_out, img_feat, txt_feat, cosine, stats, st);
   clipk::set_error("pacl_paired_fwd: bad dtype %d", dtype);
   return CLIPK_ERR_INVALID;
 }
@@ -329,6 +336,8 @@ int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P,
     return clipk::paired_bwd_t<__nv_bfloat16>(V, T, B, P, D, act, img_feat, stats, d_img, d_txt, dV, dT, st);
   if (dtype == CLIPK_F32)
     return clipk::paired_bwd_t<float>(V, T, B, P, D, act, img_feat, stats, d_img, d_txt, dV, dT, st);
+  if (dtype == CLIPK_F16)
+    return clipk::paired_bwd_t<__half>(V, T, B, P, D, act, img_feat, stats, d_img, d_txt, dV, dT, st);
   clipk::set_error("pacl_paired_bwd: bad dtype %d", dtype);
   return CLIPK_ERR_INVALID;
 }

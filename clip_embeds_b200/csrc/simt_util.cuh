@@ -24,8 +24,32 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
     v[2 * t + 1] = f.y;
   }
 }
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
 template <class T>
 __device__ __forceinline__ void store8(T* p, const float* v);
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float* v) {
+  uint4 u;
+  __half2 h0 = __floats2half2_rn(v[0], v[1]);
+  __half2 h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]);
+  __half2 h3 = __floats2half2_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 template <>
 __device__ __forceinline__ void store8<float>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -48,9 +72,62 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 template <class T> __device__ __forceinline__ float to_f(T x);
 template <> __device__ __forceinline__ float to_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <> __device__ __forceinline__ float to_f<__half>(__half x) { return __half2float(x); }
 template <class T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half(x); }
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16(x); }
+
+// Raw 8-element chunk: the load is issued now and converted when the row is consumed, so that a second row stays in
+// flight at half the register cost for 16-bit inputs.
+template <class T> struct Raw8 { uint4 q; };
+template <> struct Raw8<float> { float4 a, b; };
+template <class T>
+__device__ __forceinline__ Raw8<T> load_raw8(const T* p) {
+  Raw8<T> r;
+  r.q = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <>
+__device__ __forceinline__ Raw8<float> load_raw8<float>(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+template <class T>
+__device__ __forceinline__ Raw8<T> zero_raw8() {
+  Raw8<T> r;
+  r.q = make_uint4(0u, 0u, 0u, 0u);
+  return r;
+}
+template <>
+__device__ __forceinline__ Raw8<float> zero_raw8<float>() {
+  Raw8<float> r;
+  r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.b = r.a;
+  return r;
+}
+__device__ __forceinline__ void unpack_raw8(const Raw8<float>& r, float* v) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack_raw8(const Raw8<__nv_bfloat16>& r, float* v) {
+  const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[2 * t] = __uint_as_float(w[t] << 16);
+    v[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ void unpack_raw8(const Raw8<__half>& r, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
 
 // sum over the whole block; every thread gets the result. `red` = shared float[32].
 __device__ __forceinline__ float block_sum(float v, float* red) {

@@ -473,6 +473,9 @@ int clipk_mean_dim1(const void* X, int dtype, int B, int R, int D, float* out, v
   } else if (dtype == CLIPK_F32) {
     clipk::mean_dim1_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(X), R, D, out);
     clipk::count_launches(1);
+  } else if (dtype == CLIPK_F16) {
+    clipk::mean_dim1_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(X), R, D, out);
+    clipk::count_launches(1);
   }
   else { clipk::set_error("mean_dim1: bad dtype %d", dtype); return CLIPK_ERR_INVALID; }
   CLIPK_CHECK_CUDA(cudaGetLastError());

@@ -112,7 +112,7 @@ def gather_features(image_features, text_features, b, usehardtext, gather_with_g
     negatives of rank r occupy rows [N + r b, N + r b + counts[r]) and the rest of each b-row slab is zero padding that
     the CE kernels mask out -- nothing about the ragged sizes ever reaches the host."""
     gather = all_gather_with_grad if gather_with_grad else all_gather_nograd
-    all_img = gather(image_features, group)
+    all_img = gather(image_features, group) if image_features is not None else None   # None: the caller needs no images
     if not usehardtext:
         all_txt = gather(text_features, group)
         if not gather_with_grad and not local_loss:

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 
 ACT = {"sigmoid": 0, "sigmoid10": 0, "ones": 1, "softmax": 2, "softmax10": 2}
-_DT = {torch.bfloat16: 0, torch.float32: 1}
+_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
 
 
 def _stream():
@@ -41,7 +41,7 @@ def _f32(*shape, device):
 def _paired_forward(V, T, act, want_act=False, want_cos=False):
     _need_cuda(V, T)
     if V.dtype not in _DT:
-        raise _lib.ClipkError(f"unsupported dtype {V.dtype} (bf16 or fp32)")
+        raise _lib.ClipkError(f"unsupported dtype {V.dtype} (bf16, fp16 or fp32)")
     T = T.to(V.dtype)
     V = V.contiguous()
     T = T.contiguous()
@@ -521,6 +521,98 @@ class _FeatRowCE(torch.autograd.Function):
         if ctx.scale_needs_grad:      # d/dscale sum(dlogits * x.y) = <dX, X> / scale
             dscale = ((dX * Xc.float()).sum() / (scale_dev.reshape(()) if dev_scale else sc)).reshape(scale_shape)
         return dX.to(xdt), dY.to(ydt), dscale, dbias, None, None, None
+
+
+class _SymFeatCE(torch.autograd.Function):
+    """This rank's share of the symmetric InfoNCE from ONE logits GEMM (open_clip local-loss semantics, loss.py:137-170):
+
+        loss = 1/2 [ mean_i CE(scale X_i Y^T, off + i)  +  mean_i CE(scale Y_{off+i} Xall^T, off + i) ]
+
+    X [b,D] are this rank's images, Y [Nall,D] every caption ([N0 = W b originals | hard-negative slabs]).  The second
+    term is a COLUMN cross-entropy of the same logits over the image rows of all ranks: every rank adds up
+    exp(logit - ref) per column over its own rows, one all-reduce makes the sums global.  The backward writes
+    d(sum of all ranks' losses) / dX (complete: every column term of these rows is known locally) and this rank's partial
+    of dY (summed over the ranks by the gather's reduce-scatter) -- the image features are never gathered.
+    Assumes the same upstream gradient and the same b on every rank (true for a loss that is back-propagated as is)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, scale, bias, off, n0, slab, group):
+        _need_cuda(X, Y)
+        M, D = X.shape
+        N = Y.shape[0]
+        dev = X.device
+        st = _stream()
+        Xc, Yc = X.contiguous(), Y.contiguous()
+        if slab is not None:
+            slab_counts, slab_n0, slab_rows = slab
+            slab_counts = slab_counts.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            slab_counts, slab_n0, slab_rows = None, 0, 0
+        scale_dev = None
+        if torch.is_tensor(scale) and scale.is_cuda:
+            scale_dev = scale.detach().to(torch.float32).reshape(1).contiguous()
+            sc = 1.0
+        else:
+            sc = float(scale)
+        bi = float(bias) if bias is not None else 0.0
+        row_lse, row_loss, col_sum = _f32(M, device=dev), _f32(M, device=dev), _f32(n0, device=dev)
+        nbytes = _lib.lib().clipk_ce_feat_bwd_workspace_bytes(M, N, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_ce_sym_fwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, _p(scale_dev), _p(slab_counts), slab_n0,
+                  slab_rows, off, n0, row_lse.data_ptr(), row_loss.data_ptr(), col_sum.data_ptr(), ws.data_ptr(), nbytes, st)
+        if group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(group) > 1:
+                dist.all_reduce(col_sum, op=dist.ReduceOp.SUM, group=group)
+        s_t = scale_dev.reshape(()) if scale_dev is not None else torch.tensor(sc, device=dev)
+        col_lse = 0.5 * s_t + bi + torch.log(col_sum)                       # [n0] over the image rows of ALL ranks
+        pos = row_lse - row_loss                                            # logit of pair (i, off + i)
+        loss = 0.5 * (row_loss.mean() + (col_lse[off:off + M] - pos).mean())
+        ctx.save_for_backward(Xc, Yc, row_lse, col_lse, scale_dev if scale_dev is not None else torch.empty(0, device=dev),
+                              slab_counts if slab_counts is not None else torch.empty(0, device=dev))
+        ctx.cfg = (sc, bi, off, n0, (slab_n0, slab_rows) if slab_counts is not None else None, scale_dev is not None,
+                   torch.is_tensor(scale) and scale.requires_grad, scale.shape if torch.is_tensor(scale) else None, X.dtype,
+                   Y.dtype, torch.is_tensor(bias))
+        ctx.ws = ws
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        Xc, Yc, row_lse, col_lse, scale_dev, slab_counts = ctx.saved_tensors
+        sc, bi, off, n0, slab_geo, dev_scale, scale_grad, scale_shape, xdt, ydt, bias_tensor = ctx.cfg
+        M, D = Xc.shape
+        N = Yc.shape[0]
+        dev = Xc.device
+        w = (g.float() * (0.5 / M)).reshape(1)
+        row_w = w.expand(M).contiguous()
+        col_w = w.expand(n0).contiguous()                                   # every rank weighs its own b captions alike
+        col_bias = (torch.log(col_w) - col_lse).contiguous()
+        sl_ptr = slab_counts.data_ptr() if slab_geo is not None else 0
+        slab_n0, slab_rows = slab_geo if slab_geo is not None else (0, 0)
+        bf16_out = M <= 4096 and not scale_grad and M > 128 and N > 128
+        dX = torch.empty(M, D, dtype=torch.bfloat16 if bf16_out else torch.float32, device=dev)
+        dY = torch.empty(N, D, dtype=torch.bfloat16 if bf16_out else torch.float32, device=dev)
+        ws = ctx.ws
+        _lib.call("clipk_ce_sym_bwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, scale_dev.data_ptr() if dev_scale else 0,
+                  sl_ptr, slab_n0, slab_rows, off, n0, row_lse.data_ptr(), row_w.data_ptr(), col_bias.data_ptr(),
+                  col_w.data_ptr(), dX.data_ptr(), dY.data_ptr(), 1 if bf16_out else 0, ws.data_ptr(), ws.numel(), _stream())
+        dscale = None
+        if scale_grad:                 # d/dscale of sum(dlogits * x.y) = <dX, X> / scale
+            dscale = ((dX.float() * Xc.float()).sum() / (scale_dev.reshape(()) if dev_scale else sc)).reshape(scale_shape)
+        dbias = torch.zeros((), device=dev) if bias_tensor else None
+        return dX.to(xdt), dY.to(ydt), dscale, dbias, None, None, None, None
+
+
+def sym_feat_ce(X, Y_all, scale, bias=0.0, offset=0, n_orig=None, slab=None, group=None):
+    """See _SymFeatCE.  bf16 features with more than 128 rows / columns (CTA-pair engine); `n_orig` = number of original
+    captions at the head of Y_all (default: all of them)."""
+    n0 = Y_all.shape[0] if n_orig is None else int(n_orig)
+    return _SymFeatCE.apply(X, Y_all, scale, bias, int(offset), n0, slab, group)
+
+
+def sym_feat_ce_ok(X, Y):
+    return (X.is_cuda and X.dtype == torch.bfloat16 and Y.dtype == torch.bfloat16 and X.shape[0] > 128 and Y.shape[0] > 128
+            and X.shape[1] % 8 == 0 and os.environ.get("CLIPK_CE_SYM", "1") != "0")
 
 
 def feat_row_ce(X, Y, scale, bias=0.0, labels=None, label_offset=0, slab=None):

@@ -106,6 +106,28 @@ class OpenClipLoss(nn.Module):
     def forward(self, image_features, text_features, logit_scale, logit_bias=None, output_dict=False):
         b = image_features.shape[0]
         bias = 0.0 if logit_bias is None else logit_bias
+        sym_ok = Fk.sym_feat_ce_ok(image_features, text_features)
+        if self.world_size == 1 and sym_ok:
+            # ONE logits GEMM: the text->image CE is the column CE of the same logits over the first b columns (the
+            # originals; hard-negative rows are ignore_index rows of logits_per_text, loss.py:127-135)
+            total = Fk.sym_feat_ce(image_features, text_features, logit_scale, bias, 0, b)
+            return {"contrastive_loss": total} if output_dict else total
+        if self.world_size > 1 and self.local_loss and self.gather_with_grad and sym_ok and (
+                not self.usehardtext or b % 32 == 0):
+            # local loss, one GEMM per rank: local image rows x all captions; the column sums are all-reduced, the image
+            # features are never gathered, the caption gradient goes back through the gather's reduce-scatter
+            pg = self.group
+            off = b * self.rank
+            if self.usehardtext:
+                _, all_txt, counts = cdist.gather_features(None, text_features, b, True, True, True, self.rank,
+                                                           self.world_size, pg, keep_padding=True)
+                slab = (counts, self.world_size * b, b)
+            else:
+                all_txt = cdist.all_gather_with_grad(text_features, pg)
+                slab = None
+            total = Fk.sym_feat_ce(image_features, all_txt, logit_scale, bias, off, self.world_size * b, slab,
+                                   pg if pg is not None else torch.distributed.group.WORLD)
+            return {"contrastive_loss": total} if output_dict else total
         if self.world_size > 1:
             if self.usehardtext:
                 assert self.gather_with_grad, "usehardtext requires gather_with_grad (loss.py:77)"

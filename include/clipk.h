@@ -31,6 +31,7 @@ extern "C" {
 
 #define CLIPK_BF16 0
 #define CLIPK_F32 1
+#define CLIPK_F16 2   /* IEEE half: the paired / eval-scorer path (the reference evaluates under fp16 autocast, eval_pacl.py:53) */
 
 #define CLIPK_ACT_SIGMOID10 0 /* sigmoid(10*cos): reference parity, pacl.py:133 */
 #define CLIPK_ACT_ONES 1      /* activations overwritten with ones: the checked-in forward(), pacl.py:141-142 */
@@ -64,7 +65,7 @@ int clipk_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const
 
 /* ---------------------------------------------------------------------------------------------------------
  * PACL paired path (reference training / eval semantics; HBM-bound, one pass over V per direction).
- *   V [B / v_div, P, D], T [B, D] (dtype CLIPK_BF16 | CLIPK_F32).  Sample b uses image b / v_div
+ *   V [B / v_div, P, D], T [B, D] (dtype CLIPK_BF16 | CLIPK_F32 | CLIPK_F16; arithmetic is fp32 in every case).  Sample b uses image b / v_div
  *   (v_div = 1: paired batch; v_div = K: one image scored against K captions, eval_pacl.py:50-57).
  *   act_out [B,P] (nullable) = sigmoid(10 cos)            -> patch_alignment, pacl.py:120-133
  *   img_feat [B,D] = n(sum_p a_p V_p), txt_feat [B,D] = n(T) -> forward, pacl.py:140-145 (a := 1 for CLIPK_ACT_ONES)
@@ -160,6 +161,24 @@ int clipk_ce_feat_fwd(const void* X, const void* Y, int M, int N, int D, float s
 int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
                       const int* slab_counts, int slab_n0, int slab_rows, const int64_t* labels, int64_t label_offset, const float* row_lse, const float* row_w, float* dX,
                       int accX, float* dY, int accY, void* workspace, size_t ws_bytes, void* stream);
+
+/* Symmetric cross-entropy from ONE logits GEMM (the reference computes logits_per_image and
+ * logits_per_text with two GEMMs, open_clip/src/open_clip/loss.py:156-157, pacl.py:499-500):
+ *   rows    : X [M,D] (this rank's images), label of row m = m + label_offset            -> row_lse, row_loss [M]
+ *   columns : the first `ncol` rows of Y (the original captions of all ranks) also carry a CE over ALL image rows;
+ *             col_sum [ncol] += sum_m exp(logit[m,j] - (scale / 2 + bias))   (zeroed here; partial over THIS rank's rows:
+ *             all-reduce it over the ranks, then col_lse[j] = scale / 2 + bias + log(col_sum[j]))
+ * Backward: dL = row_w[m] (softmax_row - onehot) + (exp(logit + col_bias[j]) - col_w[lab] onehot), with
+ *   col_bias[j] = log(col_w[j]) - col_lse[j]; dX [M,D] and dY [N,D] (this rank's partial: sum it over the ranks) in fp32
+ *   (grads_bf16 = 0) or bf16 (grads_bf16 = 1, M <= 4096).  bf16 features, CTA-pair tcgen05 engine, logits never written;
+ *   workspace as clipk_ce_feat_bwd_workspace_bytes(M, N, D).  scale_dev / slab_* as above. */
+int clipk_ce_sym_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                     const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol, float* row_lse,
+                     float* row_loss, float* col_sum, void* workspace, size_t ws_bytes, void* stream);
+int clipk_ce_sym_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
+                     const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol,
+                     const float* row_lse, const float* row_w, const float* col_bias, const float* col_w, void* dX,
+                     void* dY, int grads_bf16, void* workspace, size_t ws_bytes, void* stream);
 
 /* The same backward with bf16 gradients written straight from the GEMM epilogues (dX, dY bf16, both required, no
  * accumulation); supported for 128 < M <= 4096 and N > 128 (CLIPK_ERR_INVALID otherwise: use the fp32 entry). */

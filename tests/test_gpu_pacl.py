@@ -295,3 +295,38 @@ def test_c1_paired_cliploss_full_size():
     assert torch.allclose(img.detach().cpu(), io.detach(), atol=2e-6)
     assert abs(loss.item() - lo.item()) <= 1e-5 * max(1.0, abs(lo.item()))
     assert rel_l2(V.grad.cpu(), Vo.grad) < 1e-4 and rel_l2(T.grad.cpu(), To.grad) < 1e-4
+
+
+def test_fp16_inputs_paired_and_eval_top1():
+    """fp16 features (the reference evaluates under fp16 autocast, eval_pacl.py:53; NegCLIP trains with --precision amp):
+    the paired / eval-scorer kernels take IEEE half directly (fp32 arithmetic inside).  (a) forward + backward against
+    the fp32 oracle on the same fp16-rounded inputs; (b) eval top-1 on What'sUp-shaped items: identical indices to the
+    fp32 oracle evaluated on the fp16-rounded inputs (bit-exact), and agreement with the all-fp32 pipeline reported
+    together with the smallest top-1 margin (items whose margin is below the fp16 input rounding may legitimately flip)."""
+    Fk, _ = _cuda()
+    B, P, D = 24, 576, 768
+    Vh, Th = O.rn(401, B, P, D).half(), O.rn(402, B, D).half()
+    Vo, To = Vh.float().requires_grad_(), Th.float().requires_grad_()
+    io, to = O.pacl_forward(Vo, To, "sigmoid")
+    gi, gt = O.rn(403, B, D), O.rn(404, B, D)
+    ((io * gi).sum() + (to * gt).sum()).backward()
+    V, T = Vh.cuda().requires_grad_(), Th.cuda().requires_grad_()
+    img, txt = Fk.pacl_pool(V, T, "sigmoid")
+    ((img * gi.cuda()).sum() + (txt * gt.cuda()).sum()).backward()
+    assert V.grad.dtype == torch.float16 and T.grad.dtype == torch.float16
+    assert torch.allclose(img.detach().cpu(), io.detach(), atol=1e-5) and torch.allclose(txt.detach().cpu(), to.detach(), atol=1e-5)
+    assert rel_l2(V.grad.float().cpu(), Vo.grad) < 2e-3 and rel_l2(T.grad.float().cpu(), To.grad) < 2e-3     # fp16 rounding of the stored gradient
+    # (b) eval scorer
+    items, K = 200, 4
+    Vf, Tf = O.rn(411, items, P, D), O.rn(412, items, K, D)
+    top_h, sc_h = O.eval_top1(Vf.half().float(), Tf.half().float(), 100.0)
+    top_f, sc_f = O.eval_top1(Vf, Tf, 100.0)
+    scores, top1 = Fk.pacl_eval_scores(Vf.half().cuda(), Tf.half().cuda(), 100.0)
+    assert torch.equal(top1.cpu(), top_h)                                     # bit-exact indices on identical inputs
+    assert torch.allclose(scores.cpu(), sc_h, atol=2e-4)
+    srt = sc_f.sort(dim=1, descending=True).values
+    margin = (srt[:, 0] - srt[:, 1])
+    agree = (top1.cpu() == top_f)
+    print(f"fp16 eval: agreement with the all-fp32 pipeline {agree.float().mean().item():.3f}, min margin {margin.min().item():.2e}, "
+          f"min margin among agreeing items {margin[agree].min().item():.2e}")
+    assert bool(agree[margin > 5e-2].all())          # flips only where the fp32 margin is within the input rounding
