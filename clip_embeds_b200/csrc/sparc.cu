@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "epilogues.cuh"
 #include "simt_util.cuh"
+#include "sparc_fused.cuh"
 
 namespace epi {
 // dV[b][m][n] = acc + gadd[b][n]      (gadd: broadcast gradient of the mean-pooled global feature, may be null)
@@ -344,10 +345,64 @@ static int sparc_scores_and_weights(const __nv_bfloat16* V, const __nv_bfloat16*
   return 0;
 }
 
+// The fused per-sample forward (sparc_fused.cuh) covers T <= 79 tokens, P <= 640 patches, D <= 768 in multiples of 128;
+// other shapes (and CLIPK_SPARC_FUSED=0) take the staged path below.
+static bool sparc_fused_eligible(int T, int P, int D) {
+  static const bool on = [] {
+    const char* e = getenv("CLIPK_SPARC_FUSED");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on && T < sfz::kTn && P <= 128 * sfz::kMaxMT && D <= 64 * sfz::kMaxKsD && D % 128 == 0;
+}
+
+static int sparc_fused_fwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T, int P, int D, float sigma,
+                           float* l_hat, float* g_hat, float* lnorm, float* gnorm, float4* stats, int2* arg, float* pooled,
+                           cudaStream_t st) {
+  sfz::Params pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.B = B; pr.T = T; pr.P = P; pr.D = D;
+  pr.nMT = (P + 127) / 128; pr.ksD = (D + 63) / 64; pr.kbP = (P + 63) / 64; pr.nU = D / 128;
+  pr.sigma = sigma;
+  pr.L = L; pr.l_hat = l_hat; pr.g_hat = g_hat; pr.lnorm = lnorm; pr.gnorm = gnorm; pr.stats = stats; pr.arg = arg;
+  pr.pooled = pooled;
+  sfz::Maps mp;
+  memset(&mp, 0, sizeof(mp));
+  const uint64_t ldD = (uint64_t)D * 2;
+  CLIPK_TRY(make_tmap_bf16(&mp.L, L, D, T, B, ldD, (uint64_t)T * ldD, sfz::kTn));
+  CLIPK_TRY(make_tmap_bf16(&mp.Vk, V, D, P, B, ldD, (uint64_t)P * ldD, 128));
+  CLIPK_TRY(make_tmap_bf16(&mp.Vmn, V, D, P, B, ldD, (uint64_t)P * ldD, 64));
+  static std::atomic<uint64_t> attr_mask{0};
+  int dev = 0;
+  CLIPK_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    CLIPK_CHECK_CUDA(cudaFuncSetAttribute(sfz::sparc_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sfz::kSmemTotal));
+    attr_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  const int grid = B < sm_count() ? B : sm_count();
+  const bool tr = trace_enabled();
+  if (tr) trace_begin("sparc_fused_fwd_kernel", st);
+  sfz::sparc_fused_fwd_kernel<<<grid, sfz::kThreads, sfz::kSmemTotal, st>>>(mp, pr);
+  if (tr) trace_end(st);
+  clipk::count_launches(1);
+  CLIPK_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int sparc_align_fwd(const __nv_bfloat16* V, const __nv_bfloat16* L, int B, int T, int P, int D, float sigma,
-                    float* l_hat, float* g_hat, float* lnorm, float* gnorm, void* ws, size_t ws_bytes,
+                    float* l_hat, float* g_hat, float* lnorm, float* gnorm, float* pooled, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
   CLIPK_REQUIRE(B > 0 && T > 0 && P > 0 && D > 0 && D % 8 == 0, "sparc_align_fwd: bad shape B=%d T=%d P=%d D=%d", B, T, P, D);
+  if (sparc_fused_eligible(T, P, D)) {
+    SparcWs wf{};
+    const size_t needf = sparc_carve(&wf, ws, B, T, P, D, 0);
+    CLIPK_REQUIRE(ws != nullptr && ws_bytes >= needf, "sparc_align_fwd: workspace too small (%zu < %zu)", ws_bytes, needf);
+    return sparc_fused_fwd(V, L, B, T, P, D, sigma, l_hat, g_hat, lnorm, gnorm, wf.stats, wf.arg, pooled, st);
+  }
+  if (pooled != nullptr) {
+    dim3 grid((D + 255) / 256, B);
+    mean_dim1_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(V, P, D, pooled);
+    clipk::count_launches(1);
+  }
   CLIPK_REQUIRE(T <= 128, "sparc_align_fwd: T=%d > 128 tokens is not supported", T);
   SparcWs w{};
   const size_t need = sparc_carve(&w, ws, B, T, P, D, 0);
@@ -444,10 +499,12 @@ size_t clipk_sparc_workspace_bytes(int B, int T, int P, int D, int backward) {
 }
 
 int clipk_sparc_align_fwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, float* l_hat,
-                          float* g_hat, float* lnorm, float* gnorm, void* workspace, size_t ws_bytes, void* stream) {
+                          float* g_hat, float* lnorm, float* gnorm, float* pooled, void* workspace, size_t ws_bytes,
+                          void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::sparc_align_fwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(L), B, T, P, D,
-                                sigma, l_hat, g_hat, lnorm, gnorm, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+                                sigma, l_hat, g_hat, lnorm, gnorm, pooled, workspace, ws_bytes,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int clipk_sparc_align_bwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, const float* l_hat,

@@ -640,13 +640,12 @@ class _SparcAlign(torch.autograd.Function):
         lnorm, gnorm = _f32(B, T, device=dev), _f32(B, T, device=dev)
         nbytes = _lib.lib().clipk_sparc_workspace_bytes(B, T, P, D, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.call("clipk_sparc_align_fwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, float(sigma), l_hat.data_ptr(),
-                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), ws.data_ptr(), nbytes, _stream())
-        # mean over patches of the raw V (SparcLoss's global image feature, pacl.py:561): produced here so that its
-        # gradient -- a [B,D] vector broadcast over all patches -- is added inside the dV kernel (g_add) instead of
-        # being materialised as a second dense [B,P,D] gradient and summed by autograd
+        # `pooled` = mean over patches of the raw V (SparcLoss's global image feature, pacl.py:561): produced by the same
+        # pass, so that its gradient -- a [B,D] vector broadcast over all patches -- is added inside the dV kernel (g_add)
+        # instead of being materialised as a second dense [B,P,D] gradient and summed by autograd
         pooled = _f32(B, D, device=dev)
-        _lib.call("clipk_mean_dim1", Vb.data_ptr(), _DT[Vb.dtype], B, P, D, pooled.data_ptr(), _stream())
+        _lib.call("clipk_sparc_align_fwd", Vb.data_ptr(), Lb.data_ptr(), B, T, P, D, float(sigma), l_hat.data_ptr(),
+                  g_hat.data_ptr(), lnorm.data_ptr(), gnorm.data_ptr(), pooled.data_ptr(), ws.data_ptr(), nbytes, _stream())
         ctx.save_for_backward(Vb, Lb, l_hat, g_hat, lnorm, gnorm)
         ctx.cfg = (float(sigma), V.dtype, L.dtype)
         return l_hat, g_hat, pooled

@@ -191,13 +191,16 @@ int clipk_ce_feat_bwd_bf16(const void* X, const void* Y, int M, int N, int D, fl
  * SPARC token-to-patch alignment (sparc.forward, PACL/model/pacl.py:453-478):
  *   S = L V^T (raw), min-max over patches, threshold sigma, row-normalise, G = W V; outputs l_hat = n(L),
  *   g_hat = n(G) (fp32 [B,T,D]) and their norms [B,T] (saved for backward).  V bf16 [B,P,D], L bf16 [B,T,D], T <= 128.
+ *   pooled (nullable, fp32 [B,D]) = mean over patches of V (SparcLoss's global image feature, pacl.py:561): produced by the
+ *   same pass (fused kernel: an all-ones row of the pooling GEMM).
  * Backward recomputes S / W inside `workspace`; d_g_hat, d_l_hat fp32 [B,T,D]; g_add (nullable) fp32 [B,D] is added
  * to every patch row of dV (the broadcast gradient of mean_p V from SparcLoss's global term, pacl.py:561);
  * dV [B,P,D] bf16 (dv_bf16 != 0) or fp32; dL fp32 [B,T,D].
  */
 size_t clipk_sparc_workspace_bytes(int B, int T, int P, int D, int backward);
 int clipk_sparc_align_fwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, float* l_hat,
-                          float* g_hat, float* lnorm, float* gnorm, void* workspace, size_t ws_bytes, void* stream);
+                          float* g_hat, float* lnorm, float* gnorm, float* pooled, void* workspace, size_t ws_bytes,
+                          void* stream);
 int clipk_sparc_align_bwd(const void* V, const void* L, int B, int T, int P, int D, float sigma, const float* l_hat,
                           const float* g_hat, const float* lnorm, const float* gnorm, const float* d_g_hat,
                           const float* d_l_hat, const float* g_add, void* dV, int dv_bf16, float* dL, void* workspace,
