@@ -110,5 +110,16 @@ def check(rc):
         raise ClipkError(f"clipk error {rc}: {msg.decode() if msg else '?'}")
 
 
+_NVTX = os.environ.get("CLIPK_NVTX", "0") != "0"      # NVTX range around every C-ABI call (timelines; off by default)
+
+
 def call(name, *args):
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(getattr(lib(), name)(*args))
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     check(getattr(lib(), name)(*args))

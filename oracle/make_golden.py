@@ -313,7 +313,7 @@ def main_heads():
     _close(lo2.detach(), lq.detach(), what="G10 loss")
     _close(xo2.grad, xq.grad, tol=5e-6, what="G10 dx")
     _close(yo2.grad, yq.grad, tol=5e-6, what="G10 dy")
-    G = dict(meta=dict(torch=torch.__version__, note="projection heads: outputs of the unmodified reference, CPU fp32"),
+    G = dict(meta=dict(torch=str(torch.__version__), note="projection heads: outputs of the unmodified reference, CPU fp32"),
              G7=g7(pacl), G8=dict(y=yr.detach().clone(), dx=xr.grad.clone()), G9=ref_m,
              G10=dict(loss=lq.detach().clone(), dx=xq.grad.clone(), dy=yq.grad.clone()))
     torch.save(G, os.path.join(OUT_DIR, "goldens_heads.pt"))
@@ -328,7 +328,7 @@ def main():
     pacl = refload.load_pacl()
     loss_mod = refload.load_open_clip_loss()
     G = dict(
-        meta=dict(torch=torch.__version__, note="outputs of the unmodified reference, CPU fp32"),
+        meta=dict(torch=str(torch.__version__), note="outputs of the unmodified reference, CPU fp32"),
         G1=g1(pacl, "sigmoid"), G1b=g1(pacl, "ones"), G2=g2(pacl), G3=g3(loss_mod), G4=g4(pacl),
         G5=g5(), G6=g6(pacl),
     )

@@ -15,7 +15,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def goldens():
     import torch
-    return torch.load(os.path.join(ROOT, "tests", "golden", "goldens.pt"), weights_only=False)
+    return torch.load(os.path.join(ROOT, "tests", "golden", "goldens.pt"), weights_only=True)
 
 
 def rel_l2(a, b):

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _load_g7():
-    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G7"]
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)["G7"]
 
 
 def test_heads_state_dict_keys_match_reference():
@@ -103,7 +103,7 @@ def test_rope_matches_reference_golden():
     """apply_rope (pacl.py:147-181): fp32 path against the reference's own output and gradient (golden G8; the angle
     tables are built with the reference's expressions, so only the two products per element can differ: <= 1e-6)."""
     from clip_embeds_b200.heads import apply_rope
-    G8 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G8"]
+    G8 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)["G8"]
     x = O.rn(25, 2, 50, 64).cuda().requires_grad_()
     y = apply_rope(x)
     (y * O.rn(26, 2, 50, 64).cuda()).sum().backward()

@@ -8,7 +8,7 @@ from oracle import ref_oracle as O
 
 
 def _g7():
-    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G7"]
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)["G7"]
 
 
 def test_heads_state_dict_is_the_references():

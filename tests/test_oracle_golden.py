@@ -94,7 +94,7 @@ def test_g7_projection_heads():
     """Projection heads: the restatement reproduces the reference's own modules
     (tests/golden/goldens_heads.pt, made by `python oracle/make_golden.py heads`)."""
     import os
-    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G7"]
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)["G7"]
     sd = {k: v.clone().requires_grad_() for k, v in G["vis_sd"].items()}
     sdt = {k: v.clone().requires_grad_() for k, v in G["txt_sd"].items()}
     x = O.rn(21, 3, 50, 128).requires_grad_()
@@ -111,7 +111,7 @@ def test_g7_projection_heads():
 
 def test_g8_rope():
     import os
-    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)["G8"]
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)["G8"]
     x = O.rn(25, 2, 50, 64).requires_grad_()
     y = O.apply_rope(x)
     (y * O.rn(26, 2, 50, 64)).sum().backward()
@@ -122,7 +122,7 @@ def test_g9_g10_metrics_and_vlm2vec_loss():
     """The reference's own get_clip_metrics (open_clip_train/train.py:360-377, executed unmodified from its source) and
     VLM2Vec's SimpleContrastiveLoss (src/loss.py:7-19): the restatements reproduce their outputs."""
     import os
-    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=False)
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "goldens_heads.pt"), weights_only=True)
     gq = torch.Generator().manual_seed(77)
     base = torch.randn(200, 32, generator=gq)
     gi = O.l2n(base + 2.0 * torch.randn(200, 32, generator=gq))
