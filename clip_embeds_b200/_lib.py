@@ -63,9 +63,11 @@ SIGNATURES = {
     "clipk_mean_dim1": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "clipk_normalize_rows_fwd": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "clipk_normalize_rows_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
-    "clipk_ln_fwd": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "clipk_ln_fwd": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_f32, ctypes.c_uint64, c_vp,
+                             c_vp]),
     "clipk_ln_bwd_workspace_bytes": (c_sz, [c_i64, c_int]),
-    "clipk_ln_bwd": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "clipk_ln_bwd": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_sz,
+                             c_vp]),
     "clipk_patch_proj_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clipk_patch_proj_bwd_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
     "clipk_patch_proj_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

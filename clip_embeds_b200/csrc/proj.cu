@@ -149,10 +149,37 @@ __device__ __forceinline__ void store8(float* p, const float* f) {
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row (D % 8 == 0): mean, biased variance (two passes, fp32), xn = (x - mean) rstd gamma + beta as bf16.
+// Dropout fused into the LayerNorm pass (pacl.py:72,77: Sequential(LayerNorm, Dropout(0.1), ...)).  Counter-based: the
+// keep decision of element (row, d) depends only on (seed, row * D + d), 16 random bits per element from a 32-bit
+// integer mixer, keep iff bits >= thr16 (thr16 = round(p * 65536)); one byte of keep bits per 8-element vector is saved
+// for the backward (1 bit per element instead of re-deriving or storing a bool tensor).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t vec_index, uint32_t thr16) {
+  const uint32_t lo = static_cast<uint32_t>(vec_index), hi = static_cast<uint32_t>(vec_index >> 32);
+  const uint32_t k = mix32(static_cast<uint32_t>(seed) ^ mix32(hi ^ static_cast<uint32_t>(seed >> 32)));
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t h = mix32((lo * 4u + j) ^ k);
+    bits |= ((h & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * j);
+    bits |= ((h >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return bits;
+}
+__host__ __device__ inline uint32_t dropout_thr16(float p) {
+  const float t = p * 65536.f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : static_cast<uint32_t>(t));
+}
+__host__ __device__ inline float dropout_scale(uint32_t thr16) { return 65536.f / (65536.f - static_cast<float>(thr16)); }
+
 template <typename T>
 __global__ void ln_fwd_kernel(const T* __restrict__ X, int64_t rows, int D, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ Y,
-                              float* __restrict__ mean, float* __restrict__ rstd) {
+                              float* __restrict__ mean, float* __restrict__ rstd, uint8_t* __restrict__ keep,
+                              uint32_t thr16, uint64_t seed) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -181,6 +208,14 @@ __global__ void ln_fwd_kernel(const T* __restrict__ X, int64_t rows, int D, cons
     load8<float>(beta + 8 * v, b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = fmaf((f[i] - mu) * rs, g[i], b[i]);
+    if (keep != nullptr) {
+      const uint64_t vi = (uint64_t)row * nv + v;
+      const uint32_t bits = dropout_keep8(seed, vi, thr16);
+      const float sc = dropout_scale(thr16);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = ((bits >> i) & 1u) ? f[i] * sc : 0.f;
+      keep[vi] = static_cast<uint8_t>(bits);
+    }
     store8(Y + row * D + 8 * v, f);
   }
   if (lane == 0) {
@@ -197,7 +232,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* __restrict__ G, const T* __restrict__ X,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           int64_t rows, int D, int rows_per_block,
-                                                          float* __restrict__ part) {
+                                                          float* __restrict__ part,
+                                                          const uint8_t* __restrict__ keep = nullptr, float keep_scale = 1.f) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d = blockIdx.x * 256 + 8 * lane;
@@ -211,6 +247,11 @@ __global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* _
     for (int64_t r = r0 + warp; r < r1; r += 8) {
       float g[8];
       load8<__nv_bfloat16>(G + r * D + d, g);
+      if (keep != nullptr) {
+        const uint32_t bits = keep[(r * D + d) >> 3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = ((bits >> i) & 1u) ? g[i] * keep_scale : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) sb[i] += g[i];
       if (X != nullptr) {
@@ -259,7 +300,8 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int nblk, i
 template <typename T>
 __global__ void ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ G, const T* __restrict__ X,
                                  const float* __restrict__ gamma, const float* __restrict__ mean,
-                                 const float* __restrict__ rstd, int64_t rows, int D, T* __restrict__ dX) {
+                                 const float* __restrict__ rstd, int64_t rows, int D, T* __restrict__ dX,
+                                 const uint8_t* __restrict__ keep, float keep_scale) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -271,6 +313,11 @@ __global__ void ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ G, const T* _
     load8<__nv_bfloat16>(G + row * D + 8 * v, g);
     load8<T>(X + row * D + 8 * v, x);
     load8<float>(gamma + 8 * v, ga);
+    if (keep != nullptr) {
+      const uint32_t bits = keep[(uint64_t)row * nv + v];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = ((bits >> i) & 1u) ? g[i] * keep_scale : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float gg = g[i] * ga[i];
@@ -285,6 +332,11 @@ __global__ void ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ G, const T* _
     load8<__nv_bfloat16>(G + row * D + 8 * v, g);
     load8<T>(X + row * D + 8 * v, x);
     load8<float>(gamma + 8 * v, ga);
+    if (keep != nullptr) {
+      const uint32_t bits = keep[(uint64_t)row * nv + v];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = ((bits >> i) & 1u) ? g[i] * keep_scale : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = rs * (g[i] * ga[i] - s1 - (x[i] - mu) * rs * s2);
     store8(dX + row * D + 8 * v, g);
@@ -342,10 +394,11 @@ static inline int colsum_blocks(int64_t rows) { return (int)((rows + kColsumRows
 
 template <typename T>
 static int colsum_launch(const __nv_bfloat16* G, const T* X, const float* mean, const float* rstd, int64_t rows, int D,
-                         float* part, float* out_g, float* out_b, cudaStream_t st) {
+                         float* part, float* out_g, float* out_b, cudaStream_t st, const uint8_t* keep = nullptr,
+                         float keep_scale = 1.f) {
   const int nblk = colsum_blocks(rows);
   dim3 grid((D + 255) / 256, nblk);
-  colsum_part_kernel<T><<<grid, 256, 0, st>>>(G, X, mean, rstd, rows, D, kColsumRowsPerBlock, part);
+  colsum_part_kernel<T><<<grid, 256, 0, st>>>(G, X, mean, rstd, rows, D, kColsumRowsPerBlock, part, keep, keep_scale);
   colsum_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(part, nblk, D, out_g, out_b);
   count_launches(2);
   CLIPK_CHECK_CUDA(cudaGetLastError());
@@ -430,20 +483,24 @@ extern "C" {
 
 // xn = LayerNorm(x) * gamma + beta as bf16; mean / rstd [rows] fp32 are saved for the backward.  x: bf16 | fp32.
 int clipk_ln_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta, float eps,
-                 void* xn, float* mean, float* rstd, void* stream) {
+                 void* xn, float* mean, float* rstd, float drop_p, uint64_t seed, void* keep_bits, void* stream) {
   using namespace clipk;
   CLIPK_TRY(check_device());
   CLIPK_REQUIRE(rows >= 0 && D > 0 && D % 8 == 0, "ln_fwd: bad shape rows=%lld D=%d (D %% 8 == 0)", (long long)rows, D);
   CLIPK_REQUIRE(dtype == CLIPK_BF16 || dtype == CLIPK_F32, "ln_fwd: dtype must be bf16 or fp32");
   if (rows == 0) return 0;
+  CLIPK_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "ln_fwd: dropout probability %f out of [0, 1)", drop_p);
+  CLIPK_REQUIRE(drop_p == 0.f || keep_bits != nullptr, "ln_fwd: dropout needs the keep-bit buffer (rows * D / 8 bytes)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  uint8_t* keep = drop_p > 0.f ? static_cast<uint8_t*>(keep_bits) : nullptr;
+  const uint32_t thr = dropout_thr16(drop_p);
   if (dtype == CLIPK_BF16)
     ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, D, gamma, beta, eps,
-                                                       static_cast<__nv_bfloat16*>(xn), mean, rstd);
+                                                       static_cast<__nv_bfloat16*>(xn), mean, rstd, keep, thr, seed);
   else
     ln_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), rows, D, gamma, beta, eps,
-                                               static_cast<__nv_bfloat16*>(xn), mean, rstd);
+                                               static_cast<__nv_bfloat16*>(xn), mean, rstd, keep, thr, seed);
   count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -455,8 +512,8 @@ size_t clipk_ln_bwd_workspace_bytes(int64_t rows, int D) {
 
 // dgamma, dbeta [D] fp32 from dxn (bf16 [rows, D]); dx (nullable, same dtype as x) = LayerNorm input gradient.
 int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* mean,
-                 const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, void* workspace,
-                 size_t ws_bytes, void* stream) {
+                 const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, float drop_p,
+                 const void* keep_bits, void* workspace, size_t ws_bytes, void* stream) {
   using namespace clipk;
   CLIPK_TRY(check_device());
   CLIPK_REQUIRE(rows > 0 && D > 0 && D % 8 == 0, "ln_bwd: bad shape rows=%lld D=%d", (long long)rows, D);
@@ -466,16 +523,20 @@ int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gam
   const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(dxn);
   float* part = static_cast<float*>(workspace);
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  CLIPK_REQUIRE(drop_p == 0.f || keep_bits != nullptr, "ln_bwd: dropout needs the keep bits of the forward");
+  const uint8_t* keep = drop_p > 0.f ? static_cast<const uint8_t*>(keep_bits) : nullptr;
+  const float ksc = dropout_scale(dropout_thr16(drop_p));
   if (dtype == CLIPK_BF16) {
-    CLIPK_TRY(colsum_launch<__nv_bfloat16>(g, static_cast<const __nv_bfloat16*>(x), mean, rstd, rows, D, part, dgamma, dbeta, st));
+    CLIPK_TRY(colsum_launch<__nv_bfloat16>(g, static_cast<const __nv_bfloat16*>(x), mean, rstd, rows, D, part, dgamma, dbeta, st,
+                                           keep, ksc));
     if (dx != nullptr)
       ln_bwd_dx_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g, static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
-                                                            rows, D, static_cast<__nv_bfloat16*>(dx));
+                                                            rows, D, static_cast<__nv_bfloat16*>(dx), keep, ksc);
   } else {
-    CLIPK_TRY(colsum_launch<float>(g, static_cast<const float*>(x), mean, rstd, rows, D, part, dgamma, dbeta, st));
+    CLIPK_TRY(colsum_launch<float>(g, static_cast<const float*>(x), mean, rstd, rows, D, part, dgamma, dbeta, st, keep, ksc));
     if (dx != nullptr)
       ln_bwd_dx_kernel<float><<<grid, 256, 0, st>>>(g, static_cast<const float*>(x), gamma, mean, rstd, rows, D,
-                                                    static_cast<float*>(dx));
+                                                    static_cast<float*>(dx), keep, ksc);
   }
   if (dx != nullptr) count_launches(1);
   CLIPK_CHECK_CUDA(cudaGetLastError());

@@ -8,9 +8,10 @@ The modules keep the reference's constructor arguments, sub-module names and sta
 `linear_projection` / `text_projection` alias of ONE Linear, pacl.py:39), so a reference checkpoint loads with
 `load_state_dict`.  Parameters stay fp32 masters; every call casts the (small) weight matrices to bf16 and runs
 LayerNorm, the GEMMs (bias / GELU / GELU' fused into the tcgen05 epilogues) and all gradients in libclipk.  The output
-is bf16 (what the scorer consumes); there is no eager fallback.  Dropout in training mode is applied with
-`torch.nn.functional.dropout` on the normalised activations (torch's Philox stream, as in the reference); in eval mode
-it is the identity.
+is bf16 (what the scorer consumes); there is no eager fallback.  Dropout (training mode, pacl.py:72,77) is FUSED into
+the LayerNorm kernel: a counter-based mask drawn in the kernel from a seed of torch's CPU generator, kept as one bit
+per element and replayed by the backward (the reference's own Philox stream cannot be reproduced bit-wise by any fused
+mask; the tests replay OUR mask through the CPU restatement).  In eval mode it is the identity.
 """
 import torch
 import torch.nn as nn
@@ -25,10 +26,11 @@ def _rows(x):
 
 
 class _LayerNormBf16(torch.autograd.Function):
-    """xn = LayerNorm(x) as bf16 rows; x bf16 | fp32 [..., D]."""
+    """xn = Dropout_p(LayerNorm(x)) as bf16 rows; x bf16 | fp32 [..., D].  p = 0: plain LayerNorm.  The dropout mask is
+    drawn inside the kernel (counter-based on `seed`), kept as one bit per element and replayed by the backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, drop_p=0.0, seed=0):
         _need_cuda(x)
         if x.dtype not in _DT or x.dtype == torch.float16:
             x = x.float()
@@ -38,16 +40,22 @@ class _LayerNormBf16(torch.autograd.Function):
         g, b = weight.float().contiguous(), bias.float().contiguous()
         xn = torch.empty(R, D, dtype=torch.bfloat16, device=x.device)
         mean, rstd = _f32(R, device=x.device), _f32(R, device=x.device)
+        keep = torch.empty(R * D // 8, dtype=torch.uint8, device=x.device) if drop_p > 0 else None
         _lib.call("clipk_ln_fwd", x2.data_ptr(), _DT[x2.dtype], R, D, g.data_ptr(), b.data_ptr(), float(eps),
-                  xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream())
-        ctx.save_for_backward(x2, g, mean, rstd)
+                  xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), float(drop_p), int(seed) & (2 ** 64 - 1),
+                  0 if keep is None else keep.data_ptr(), _stream())
+        ctx.save_for_backward(x2, g, mean, rstd, keep if keep is not None else torch.empty(0, device=x.device))
         ctx.lead = lead
         ctx.wdt = (weight.dtype, bias.dtype)
+        ctx.drop_p = float(drop_p)
+        ctx.mark_non_differentiable(*([keep] if keep is not None else []))
+        if keep is not None:
+            return xn.reshape(*lead, D), keep
         return xn.reshape(*lead, D)
 
     @staticmethod
-    def backward(ctx, dxn):
-        x2, g, mean, rstd = ctx.saved_tensors
+    def backward(ctx, dxn, *_unused):
+        x2, g, mean, rstd, keep = ctx.saved_tensors
         R, D = x2.shape
         dxn2 = dxn.reshape(R, D).to(torch.bfloat16).contiguous()
         dgamma, dbeta = _f32(D, device=x2.device), _f32(D, device=x2.device)
@@ -56,12 +64,30 @@ class _LayerNormBf16(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)
         _lib.call("clipk_ln_bwd", x2.data_ptr(), _DT[x2.dtype], R, D, g.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                   dxn2.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0 if dx is None else dx.data_ptr(),
-                  ws.data_ptr(), nbytes, _stream())
-        return (None if dx is None else dx.reshape(*ctx.lead, D), dgamma.to(ctx.wdt[0]), dbeta.to(ctx.wdt[1]), None)
+                  ctx.drop_p, keep.data_ptr() if ctx.drop_p > 0 else 0, ws.data_ptr(), nbytes, _stream())
+        return (None if dx is None else dx.reshape(*ctx.lead, D), dgamma.to(ctx.wdt[0]), dbeta.to(ctx.wdt[1]), None,
+                None, None)
 
 
-def layer_norm_bf16(x, weight, bias, eps=1e-5):
-    return _LayerNormBf16.apply(x, weight, bias, eps)
+def layer_norm_bf16(x, weight, bias, eps=1e-5, drop_p=0.0, seed=0, return_mask=False):
+    """bf16 LayerNorm rows with the reference's Dropout fused behind it (training mode: `drop_p` > 0).  `return_mask`
+    additionally returns the keep bits (uint8 [rows * D / 8], bit j of byte v = element 8 v + j) for mask-replay tests."""
+    if drop_p > 0:
+        xn, keep = _LayerNormBf16.apply(x, weight, bias, eps, float(drop_p), int(seed))
+        return (xn, keep) if return_mask else xn
+    xn = _LayerNormBf16.apply(x, weight, bias, eps)
+    return (xn, None) if return_mask else xn
+
+
+def _dropout_seed():
+    """A fresh 63-bit seed from torch's CPU generator (follows torch.manual_seed; no device synchronisation)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def unpack_keep_bits(keep, shape):
+    """keep bits of `layer_norm_bf16(..., return_mask=True)` -> bool tensor of `shape` (test / debugging helper)."""
+    bits = (keep.reshape(-1, 1) >> torch.arange(8, device=keep.device, dtype=torch.uint8)) & 1
+    return bits.reshape(shape).bool()
 
 
 class _PatchProj(torch.autograd.Function):
@@ -168,9 +194,8 @@ class VisualProjection(nn.Sequential):
 
     def forward(self, x):
         ln, drop, proj = self[0], self[1], self[2]
-        xn = layer_norm_bf16(x, ln.weight, ln.bias, ln.eps)
-        if self.training and drop.p > 0:
-            xn = torch.nn.functional.dropout(xn, drop.p, True)
+        p = drop.p if self.training else 0.0
+        xn = layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, _dropout_seed() if p > 0 else 0)     # dropout fused in
         return proj(xn)
 
 
@@ -182,9 +207,8 @@ class TextProjection(nn.Sequential):
 
     def forward(self, x):
         ln, drop, lin = self[0], self[1], self[2]
-        xn = layer_norm_bf16(x, ln.weight, ln.bias, ln.eps)
-        if self.training and drop.p > 0:
-            xn = torch.nn.functional.dropout(xn, drop.p, True)
+        p = drop.p if self.training else 0.0
+        xn = layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, _dropout_seed() if p > 0 else 0)
         return _Linear.apply(xn, lin.weight, lin.bias)
 
 

@@ -229,6 +229,10 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
  * Rows are tokens.  x: bf16 | fp32 [rows, D] (dtype enum); xn bf16; gamma, beta, mean, rstd fp32.
  *   clipk_ln_fwd : xn = (x - mean) rstd gamma + beta, saves mean / rstd (biased variance, eps inside the sqrt)
  *   clipk_ln_bwd : dgamma, dbeta [D] from dxn (bf16); dx (nullable; dtype of x) = gradient wrt the LayerNorm input
+ *   Dropout (pacl.py:72,77) is fused into both: drop_p > 0 zeroes each element of xn with probability drop_p (rounded
+ *   to a multiple of 2^-16) and scales the others by 1 / (1 - drop_p); the decision of element i depends only on
+ *   (seed, i).  keep_bits [rows * D / 8] bytes receives one keep bit per element (bit j of byte v = element 8 v + j) and
+ *   is handed back to clipk_ln_bwd, which masks / scales dxn before the LayerNorm Jacobian.  drop_p = 0: identity.
  * Patch_Projection: y = W1 xn + b1 + W3 gelu(W2 xn + b2) + b3 (erf GELU).  Weights bf16 [out, in], biases fp32,
  * b13 = b1 + b3.  fwd writes Gp = gelu'(z), H = gelu(z) (saved for the backward) and Y (all bf16 [R, Dout]); bwd
  * consumes dY (bf16) and writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
@@ -239,11 +243,11 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
 int clipk_rope(const void* x, int dtype_in, int64_t rows, int S, int D, const float* sin_t, const float* cos_t, void* y,
                int dtype_out, int inverse, void* stream);
 int clipk_ln_fwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* beta, float eps,
-                 void* xn, float* mean, float* rstd, void* stream);
+                 void* xn, float* mean, float* rstd, float drop_p, uint64_t seed, void* keep_bits, void* stream);
 size_t clipk_ln_bwd_workspace_bytes(int64_t rows, int D);
 int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gamma, const float* mean,
-                 const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, void* workspace,
-                 size_t ws_bytes, void* stream);
+                 const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, float drop_p,
+                 const void* keep_bits, void* workspace, size_t ws_bytes, void* stream);
 int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const void* W1, const void* W2, const void* W3,
                          const float* b13, const float* b2, void* Gp, void* H, void* Y, void* stream);
 size_t clipk_patch_proj_bwd_workspace_bytes(int64_t R, int Din, int Dout);

@@ -142,3 +142,50 @@ def test_llm2pacl_c5_heads_to_eval_scorer():
     agree = (top1.cpu() == top_o).float().mean().item()
     print(f"C5 heads -> eval scorer: top-1 agreement with the all-fp32 oracle pipeline {agree:.3f}")
     assert agree >= 0.9                                                                    # (3)
+
+
+def test_training_mode_dropout_fused_mask_replay():
+    """Training mode (pacl.py:72: Dropout(0.1) between LayerNorm and Patch_Projection): the dropout mask is drawn inside
+    the LayerNorm kernel and kept as one bit per element.  (a) the keep rate is 1 - p within 4 sigma and differs between
+    seeds; (b) MASK REPLAY: the same mask applied in the oracle's visual_projection reproduces the CUDA output, the input
+    gradient and every parameter gradient within the bf16 tolerances of the eval-mode test."""
+    from clip_embeds_b200 import heads
+    from oracle import ref_oracle as O
+    torch.manual_seed(0)
+    B, S, Din, Dout, p = 4, 50, 256, 128, 0.1
+    mod = heads.VisualProjection(Din, Dout, p).cuda().train()
+    x0 = O.rn(501, B, S, Din)
+    x = x0.cuda().requires_grad_()
+    ln = mod[0]
+    xn, keep = heads.layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, 1234, return_mask=True)
+    mask = heads.unpack_keep_bits(keep, (B, S, Din))
+    rate = mask.float().mean().item()
+    n = mask.numel()
+    assert abs(rate - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5 + 1e-4, rate
+    _, keep2 = heads.layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, 99, return_mask=True)
+    assert not torch.equal(keep, keep2)
+    _, keep3 = heads.layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, 1234, return_mask=True)
+    assert torch.equal(keep, keep3)                      # the mask is a pure function of (seed, element index)
+    # forward + backward through the fused path with that mask
+    y = mod[2](xn)
+    gy = O.rn(502, B, S, Dout).cuda()
+    (y.float() * gy).sum().backward()
+    # oracle with the replayed mask (fp32): LayerNorm -> mask / (1 - p_eff) -> Patch_Projection
+    sd = {k: v.detach().cpu().float() for k, v in mod.state_dict().items()}
+    xo = x0.clone().requires_grad_()
+    params = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    thr = int(p * 65536 + 0.5)
+    scale = 65536.0 / (65536.0 - thr)
+    xno = O.layer_norm(xo, params["0.weight"], params["0.bias"]) * mask.cpu().float() * scale
+    yo = O.patch_projection(xno, params, prefix="2.")
+    (yo * gy.cpu()).sum().backward()
+    assert (y.float().cpu() - yo.detach()).abs().max().item() < 3e-2 * max(1.0, yo.detach().abs().max().item())
+    assert rel_l2(x.grad.cpu(), xo.grad) < 3e-2
+    for k, prm in mod.named_parameters():
+        if prm.grad is not None and k in params and params[k].grad is not None:
+            assert rel_l2(prm.grad.cpu().float(), params[k].grad) < 4e-2, k
+    # the module itself in train mode: different calls draw different masks, eval mode is deterministic
+    y1, y2 = mod(x.detach()), mod(x.detach())
+    assert not torch.equal(y1, y2)
+    mod.eval()
+    assert torch.equal(mod(x.detach()), mod(x.detach()))
