@@ -25,7 +25,7 @@ SIGNATURES = {
                                       c_vp, c_vp]),
     "clipk_pacl_allpairs_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "clipk_pacl_allpairs_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
-                                        c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
+                                        c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_int, c_vp]),
     "clipk_pacl_allpairs_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp]),
     "clipk_ce_rows": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -68,7 +68,8 @@ SIGNATURES = {
     "clipk_ln_bwd_workspace_bytes": (c_sz, [c_i64, c_int]),
     "clipk_ln_bwd": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_sz,
                              c_vp]),
-    "clipk_patch_proj_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "clipk_patch_proj_fwd": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp]),
     "clipk_patch_proj_bwd_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
     "clipk_patch_proj_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -550,10 +550,10 @@ static int fused_fwd_launch(const __nv_bfloat16* V, const __nv_bfloat16* That, i
 
 int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt, int P, int D, int act, float c,
                  float* rnV, float* rnT, float* num, float* usq, float* scores, __nv_bfloat16* pooled, void* ws,
-                 size_t ws_bytes, int group, int lanes, cudaStream_t st) {
+                 size_t ws_bytes, int group, int lanes, int rnv_given, cudaStream_t st) {
   CLIPK_TRY(validate(Bi, Bt, P, D, act, group));
   if (group <= 0) {
-    CLIPK_REQUIRE(pooled == nullptr, "pacl_allpairs_fwd: the persistent kernel (group <= 0) does not save pooled vectors");
+    CLIPK_REQUIRE(pooled == nullptr && !rnv_given, "pacl_allpairs_fwd: the persistent kernel (group <= 0) does not save pooled vectors");
     return mega_fwd(V, T, Bi, Bt, P, D, act, c, rnV, rnT, num, usq, scores, ws, ws_bytes, group, lanes, st);
   }
   CLIPK_REQUIRE(lanes >= 1 && lanes <= kMaxLanes, "pacl_allpairs: lanes must be in [1, %d]", kMaxLanes);
@@ -564,9 +564,14 @@ int allpairs_fwd(const __nv_bfloat16* V, const __nv_bfloat16* T, int Bi, int Bt,
   const size_t need = ap_carve(w, &sh, ws, Bi, Bt, P, D, group, lanes, 0, save, fused);
   CLIPK_REQUIRE(ws != nullptr && ws_bytes >= need, "pacl_allpairs_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
   const int Ppad = round_up(P, 64);
-  rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
+  // rnV given: the producer of V (the projection head's output GEMM) already emitted the row norms -- one pass over the
+  // 906 MB patch tensor less
+  if (!rnv_given) {
+    rownorm_bf16_kernel<<<(unsigned)(((int64_t)Bi * P + 7) / 8), 256, 0, st>>>(V, (int64_t)Bi * P, D, rnV);
+    count_launches(1);
+  }
   rownorm_bf16_kernel<<<(Bt + 7) / 8, 256, 0, st>>>(T, Bt, D, rnT);
-  count_launches(2);
+  count_launches(1);
   if (save || fused) {
     that_bf16_kernel<<<(unsigned)(((int64_t)Bt * D / 8 + 255) / 256), 256, 0, st>>>(T, rnT, Bt, D, sh.That);
     count_launches(1);
@@ -887,11 +892,11 @@ size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int gro
 
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
                             float* rnT, float* num, float* usq, float* scores, void* pooled, void* workspace,
-                            size_t ws_bytes, int group, int lanes, void* stream) {
+                            size_t ws_bytes, int group, int lanes, int rnv_given, void* stream) {
   CLIPK_TRY(clipk::check_device());
   return clipk::allpairs_fwd(static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(T), Bi, Bt, P, D,
                              act, c, rnV, rnT, num, usq, scores, static_cast<__nv_bfloat16*>(pooled), workspace,
-                             ws_bytes, group, lanes, static_cast<cudaStream_t>(stream));
+                             ws_bytes, group, lanes, rnv_given, static_cast<cudaStream_t>(stream));
 }
 
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,

@@ -68,7 +68,8 @@ struct BiasGelu2 {
   __device__ void tile_end(int, int, int, int, int) {}
 };
 
-// out = bf16(acc + bias[n])
+// out = bf16(acc + bias[n]);  optionally rowsq[m] += sum_n out[m][n]^2 over the bf16-ROUNDED outputs: the squared row norms
+// the PACL scorer needs of its patch tensor (F.normalize, pacl.py:122), so that it does not have to read V once more
 struct BiasTma {
   static constexpr bool kTmaOut = true;
   using Side = float;
@@ -76,19 +77,33 @@ struct BiasTma {
     eng::OutDesc out;
     const float* bias;   // [N] or nullptr
     int N;
+    float* rowsq;        // [M] or nullptr (zeroed by the caller)
+    int M;
   };
   Params p;
-  __device__ explicit BiasTma(const Params& pp) : p(pp) {}
-  __device__ void tile_begin(int, int, int) {}
+  float sq;
+  __device__ explicit BiasTma(const Params& pp) : p(pp), sq(0.f) {}
+  __device__ void tile_begin(int, int, int) { sq = 0.f; }
   __device__ Side pre(int, int, int n) const {
     const int lane = (int)ptx::lane_id();
     return (p.bias != nullptr && n + lane < p.N) ? __ldg(p.bias + n + lane) : 0.f;
   }
-  __device__ void chunk(int, int, int, float* v, const Side& b_l) {
+  __device__ void chunk(int, int, int n, float* v, const Side& b_l) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, b_l, j);
+    if (p.rowsq != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const uint32_t pk = ptx::pack_bf16x2(v[j], v[j + 1]);          // the values the store will write
+        const float a0 = __uint_as_float(pk << 16), a1 = __uint_as_float(pk & 0xFFFF0000u);
+        if (n + j < p.N) sq = fmaf(a0, a0, sq);
+        if (n + j + 1 < p.N) sq = fmaf(a1, a1, sq);
+      }
+    }
   }
-  __device__ void tile_end(int, int, int, int, int) {}
+  __device__ void tile_end(int, int m, int, int, int) {
+    if (p.rowsq != nullptr && m < p.M) atomicAdd(p.rowsq + m, sq);
+  }
 };
 
 // acc = dY W3 (= dH);  dZ = dH * gelu'(z): the derivative chunks (stored by the forward) arrive through TMA
@@ -580,7 +595,7 @@ int clipk_rope(const void* x, int dtype_in, int64_t rows, int S, int D, const fl
 // b13 = b1 + b3, b2: fp32 [Dout].  Outputs (bf16 [R, Dout]): Gp = gelu'(z), H = gelu(z) (both saved for the
 // backward), Y.
 int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const void* W1, const void* W2, const void* W3,
-                         const float* b13, const float* b2, void* Gp, void* H, void* Y, void* stream) {
+                         const float* b13, const float* b2, void* Gp, void* H, void* Y, float* ysq, void* stream) {
   using namespace clipk;
   CLIPK_TRY(check_device());
   CLIPK_TRY(check_rows(R));
@@ -603,7 +618,8 @@ int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const voi
     a[1].ptr = H; a[1].rows = M; a[1].k = Dout; a[1].ld = Dout;
     b[1].ptr = W3; b[1].rows = Dout; b[1].k = Dout; b[1].ld = Dout;
     const int ks[2] = {(Din + 63) / 64, (Dout + 63) / 64};
-    epi::BiasTma::Params ep{{Y, Dout, (int64_t)M * Dout, M, Dout, 1}, b13, Dout};
+    if (ysq != nullptr) CLIPK_CHECK_CUDA(cudaMemsetAsync(ysq, 0, (size_t)M * 4, st));
+    epi::BiasTma::Params ep{{Y, Dout, (int64_t)M * Dout, M, Dout, 1}, b13, Dout, ysq, M};
     CLIPK_TRY((launch_gemm2<256, false, false, epi::BiasTma>(a, b, 2, ks, ks, M, Dout, 1, ep, st)));
   }
   return 0;

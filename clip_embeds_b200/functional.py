@@ -156,7 +156,7 @@ def _save_pooled(Bi, Bt, D, g, needs_grad):
 
 class _PaclAllPairs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, V, T, c, act, group):
+    def forward(ctx, V, T, c, act, group, v_sqnorm=None):
         _need_cuda(V, T)
         Vb = V.to(torch.bfloat16).contiguous()
         Tb = T.to(torch.bfloat16).contiguous()
@@ -167,14 +167,18 @@ class _PaclAllPairs(torch.autograd.Function):
         needs_grad = any(ctx.needs_input_grad[:2])
         gb, _ = _resolve(group, Bi, Bt, P, D, True)
         save = _save_pooled(Bi, Bt, D, min(g, gb), needs_grad)
-        rnV, rnT = _f32(Bi, P, device=dev), _f32(Bt, device=dev)
+        if v_sqnorm is not None:      # squared row norms from the producer of V (the head's output GEMM): no pass over V
+            rnV = v_sqnorm.detach().float().reshape(Bi, P).clamp_min(1e-24).rsqrt().contiguous()
+        else:
+            rnV = _f32(Bi, P, device=dev)
+        rnT = _f32(Bt, device=dev)
         num, usq, scores = _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev), _f32(Bi, Bt, device=dev)
         pooled = torch.empty(Bi, Bt, D, dtype=torch.bfloat16, device=dev) if save else None
         nbytes = _lib.lib().clipk_pacl_allpairs_workspace_bytes(Bi, Bt, P, D, g, lanes, 2 if save else 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.call("clipk_pacl_allpairs_fwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
                   rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), scores.data_ptr(), _p(pooled), ws.data_ptr(), nbytes,
-                  g, lanes, _stream())
+                  g, lanes, 1 if v_sqnorm is not None else 0, _stream())
         if save:
             ctx.save_for_backward(Vb, Tb, rnV, rnT, num, usq, pooled)
         else:
@@ -202,14 +206,16 @@ class _PaclAllPairs(torch.autograd.Function):
         _lib.call("clipk_pacl_allpairs_bwd", Vb.data_ptr(), Tb.data_ptr(), Bi, Bt, P, D, act, c, rnV.data_ptr(),
                   rnT.data_ptr(), num.data_ptr(), usq.data_ptr(), dscores.data_ptr(), _p(pooled), dV.data_ptr(),
                   dT.data_ptr(), ws.data_ptr(), nbytes, g, lanes, _stream())
-        return dV.to(v_dtype), dT.to(t_dtype), None, None, None
+        return dV.to(v_dtype), dT.to(t_dtype), None, None, None, None
 
 
-def pacl_scores(visual_proj, text_proj, c=1.0, activation="sigmoid", group=None):
+def pacl_scores(visual_proj, text_proj, c=1.0, activation="sigmoid", group=None, v_sqnorm=None):
     """All-pairs text-conditioned scores [Bi,Bt] = c * cos(pool(V_i | t_k), t_k) (bf16 tensor cores, fp32
     accumulation).  Inputs are cast to bf16; gradients come back in the input dtypes.
-    `group`: None (default schedule), images-per-group, or (images-per-group, lanes)."""
-    return _PaclAllPairs.apply(visual_proj, text_proj, float(c), ACT[activation], group)
+    `group`: None (default schedule), images-per-group, or (images-per-group, lanes).
+    `v_sqnorm` [Bi,P] (optional): squared L2 norms of the patch rows as emitted by `heads.VisualProjection(...,
+    return_sqnorm=True)`; the scorer then skips its own norm pass over V."""
+    return _PaclAllPairs.apply(visual_proj, text_proj, float(c), ACT[activation], group, v_sqnorm)
 
 
 # --------------------------------------------------------------------------------------------- CE on a score matrix

@@ -94,7 +94,7 @@ class _PatchProj(torch.autograd.Function):
     """y = W1 xn + b1 + W3 gelu(W2 xn + b2) + b3 on bf16 rows (pacl.py:47-48)."""
 
     @staticmethod
-    def forward(ctx, xn, W1, b1, W2, b2, W3, b3):
+    def forward(ctx, xn, W1, b1, W2, b2, W3, b3, want_sqnorm=False):
         _need_cuda(xn)
         x2, lead = _rows(xn)
         x2 = x2.to(torch.bfloat16).contiguous()
@@ -107,15 +107,20 @@ class _PatchProj(torch.autograd.Function):
         Gp = torch.empty(R, Dout, dtype=torch.bfloat16, device=dev)      # gelu'(z), saved for the backward
         H = torch.empty_like(Gp)
         Y = torch.empty_like(Gp)
+        ysq = _f32(R, device=dev) if want_sqnorm else None
         _lib.call("clipk_patch_proj_fwd", x2.data_ptr(), R, Din, Dout, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(),
-                  b13.data_ptr(), b2f.data_ptr(), Gp.data_ptr(), H.data_ptr(), Y.data_ptr(), _stream())
+                  b13.data_ptr(), b2f.data_ptr(), Gp.data_ptr(), H.data_ptr(), Y.data_ptr(),
+                  0 if ysq is None else ysq.data_ptr(), _stream())
         ctx.save_for_backward(x2, Gp, H, w1, w2, w3)
         ctx.lead = lead
         ctx.dts = tuple(t.dtype for t in (xn, W1, b1, W2, b2, W3, b3))
+        if want_sqnorm:
+            ctx.mark_non_differentiable(ysq)
+            return Y.reshape(*lead, Dout), ysq.reshape(*lead)
         return Y.reshape(*lead, Dout)
 
     @staticmethod
-    def backward(ctx, dY):
+    def backward(ctx, dY, *_unused):
         x2, Gp, H, w1, w2, w3 = ctx.saved_tensors
         R, Din = x2.shape
         Dout = w1.shape[0]
@@ -132,7 +137,7 @@ class _PatchProj(torch.autograd.Function):
                   dW2.data_ptr(), dW3.data_ptr(), db13.data_ptr(), db2.data_ptr(), ws.data_ptr(), nbytes, _stream())
         dt = ctx.dts
         return (None if dxn is None else dxn.reshape(*ctx.lead, Din).to(dt[0]), dW1.to(dt[1]), db13.to(dt[2]),
-                dW2.to(dt[3]), db2.to(dt[4]), dW3.to(dt[5]), db13.to(dt[6]))
+                dW2.to(dt[3]), db2.to(dt[4]), dW3.to(dt[5]), db13.to(dt[6]), None)
 
 
 class _Linear(torch.autograd.Function):
@@ -180,9 +185,12 @@ class Patch_Projection(nn.Module):
         self.linear_projection = self.text_projection = nn.Sequential(nn.Linear(in_dim, out_dim))
         self.non_linear_projection = nn.Sequential(nn.Linear(in_dim, out_dim), nn.GELU(), nn.Linear(out_dim, out_dim))
 
-    def forward(self, x):
+    def forward(self, x, return_sqnorm=False):
+        """return_sqnorm: also return the squared L2 norm of every output row ([...] fp32), accumulated in the epilogue of
+        the output GEMM -- hand it to `functional.pacl_scores(..., v_sqnorm=)` / `PaclAllPairsLoss` and the scorer skips
+        its own pass over the patch tensor."""
         lin, nl0, nl2 = self.linear_projection[0], self.non_linear_projection[0], self.non_linear_projection[2]
-        return _PatchProj.apply(x, lin.weight, lin.bias, nl0.weight, nl0.bias, nl2.weight, nl2.bias)
+        return _PatchProj.apply(x, lin.weight, lin.bias, nl0.weight, nl0.bias, nl2.weight, nl2.bias, return_sqnorm)
 
 
 class VisualProjection(nn.Sequential):
@@ -192,11 +200,11 @@ class VisualProjection(nn.Sequential):
     def __init__(self, in_dim=1024, out_dim=768, p=0.1):
         super().__init__(nn.LayerNorm(in_dim), nn.Dropout(p), Patch_Projection(in_dim, out_dim))
 
-    def forward(self, x):
+    def forward(self, x, return_sqnorm=False):
         ln, drop, proj = self[0], self[1], self[2]
         p = drop.p if self.training else 0.0
         xn = layer_norm_bf16(x, ln.weight, ln.bias, ln.eps, p, _dropout_seed() if p > 0 else 0)     # dropout fused in
-        return proj(xn)
+        return proj(xn, return_sqnorm)
 
 
 class TextProjection(nn.Sequential):

@@ -53,7 +53,8 @@ class PaclAllPairsLoss(nn.Module):
         self.image_group = image_group
         self.grad_reduction = grad_reduction
 
-    def forward(self, visual_proj, text_proj):
+    def forward(self, visual_proj, text_proj, v_sqnorm=None):
+        """v_sqnorm (optional): squared row norms of `visual_proj` from `heads.VisualProjection(x, return_sqnorm=True)`."""
         pg = self.group
         if pg is not None and cdist.world_size(pg) > 1:
             all_text = cdist.all_gather_with_grad(text_proj, pg)
@@ -62,7 +63,7 @@ class PaclAllPairsLoss(nn.Module):
             pg = None
             all_text = text_proj
             offset = 0
-        scores = Fk.pacl_scores(visual_proj, all_text, self.logit_scale, self.activation, self.image_group)
+        scores = Fk.pacl_scores(visual_proj, all_text, self.logit_scale, self.activation, self.image_group, v_sqnorm)
         loss = Fk.score_infonce(scores, offset, pg)
         if pg is not None and self.grad_reduction == "mean":
             loss = cdist.scale_grad(loss, cdist.world_size(pg))

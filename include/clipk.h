@@ -92,11 +92,13 @@ int clipk_pacl_paired_bwd(const void* V, const void* T, int dtype, int B, int P,
  * instead of 8; SURVEY 7.3-5 "store U as bf16").  Pass the same buffer (or NULL both times) to fwd and bwd.
  * Backward: dscores [Bi,Bt] -> dV bf16 [Bi,P,D], dT fp32 [Bt,D] (gradient w.r.t. the raw T).
  * workspace_bytes `mode`: bit 0 = backward, bit 1 = pooled.
+ * rnv_given != 0: `rnV` already holds 1 / max(|V_ip|, 1e-12) (the projection head's output GEMM emits the squared row
+ * norms, clipk_patch_proj_fwd `ysq`): the forward then skips its own pass over V.
  */
 size_t clipk_pacl_allpairs_workspace_bytes(int Bi, int Bt, int P, int D, int group, int lanes, int mode);
 int clipk_pacl_allpairs_fwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c, float* rnV,
                             float* rnT, float* num, float* usq, float* scores, void* pooled, void* workspace,
-                            size_t ws_bytes, int group, int lanes, void* stream);
+                            size_t ws_bytes, int group, int lanes, int rnv_given, void* stream);
 int clipk_pacl_allpairs_bwd(const void* V, const void* T, int Bi, int Bt, int P, int D, int act, float c,
                             const float* rnV, const float* rnT, const float* num, const float* usq,
                             const float* dscores, const void* pooled, void* dV, float* dT, void* workspace,
@@ -236,6 +238,8 @@ int clipk_normalize_rows_bwd(const float* xh, const float* g, const float* norm,
  * Patch_Projection: y = W1 xn + b1 + W3 gelu(W2 xn + b2) + b3 (erf GELU).  Weights bf16 [out, in], biases fp32,
  * b13 = b1 + b3.  fwd writes Gp = gelu'(z), H = gelu(z) (saved for the backward) and Y (all bf16 [R, Dout]); bwd
  * consumes dY (bf16) and writes dxn (nullable, bf16 [R, Din]) and fp32 weight / bias gradients (db13 = db1 = db3).
+ * ysq (nullable, fp32 [R]): squared L2 norm of every (bf16-rounded) output row, accumulated in the epilogue of the output
+ * GEMM -- the row norms the PACL scorer needs of its patch tensor (pacl.py:122) without another pass over Y.
  * clipk_linear_*: y = x W^T + b on bf16 rows, dx (nullable) bf16, dW / db fp32. */
 /* apply_rope (PACL/model/pacl.py:147-181) on token rows [B*S, D]: pairs (x[2j], x[2j+1]) rotated by
  * the angle of (position = row % S, j), written de-interleaved (first halves, then second halves).  sin_t / cos_t: fp32
@@ -249,7 +253,7 @@ int clipk_ln_bwd(const void* x, int dtype, int64_t rows, int D, const float* gam
                  const float* rstd, const void* dxn, float* dgamma, float* dbeta, void* dx, float drop_p,
                  const void* keep_bits, void* workspace, size_t ws_bytes, void* stream);
 int clipk_patch_proj_fwd(const void* xn, int64_t R, int Din, int Dout, const void* W1, const void* W2, const void* W3,
-                         const float* b13, const float* b2, void* Gp, void* H, void* Y, void* stream);
+                         const float* b13, const float* b2, void* Gp, void* H, void* Y, float* ysq, void* stream);
 size_t clipk_patch_proj_bwd_workspace_bytes(int64_t R, int Din, int Dout);
 int clipk_patch_proj_bwd(const void* xn, const void* Gp, const void* H, const void* dY, int64_t R, int Din, int Dout,
                          const void* W1, const void* W2, const void* W3, void* dxn, float* dW1, float* dW2, float* dW3,

@@ -189,3 +189,28 @@ def test_training_mode_dropout_fused_mask_replay():
     assert not torch.equal(y1, y2)
     mod.eval()
     assert torch.equal(mod(x.detach()), mod(x.detach()))
+
+
+def test_head_emits_row_norms_for_the_scorer():
+    """§8f-1: the head's output GEMM emits the squared norm of every projected patch row (of the bf16-rounded values);
+    the all-pairs scorer fed with them skips its own norm pass and returns the same scores and gradients."""
+    import clip_embeds_b200.functional as Fk
+    from clip_embeds_b200 import heads
+    torch.manual_seed(1)
+    B, S, Din, Dout = 6, 196, 256, 128
+    vis = heads.VisualProjection(Din, Dout).cuda().eval()
+    x = O.rn(601, B, S, Din).cuda()
+    T = O.rn(602, 40, Dout).cuda().to(torch.bfloat16).requires_grad_()
+    V, sq = vis(x, return_sqnorm=True)
+    want = V.detach().float().pow(2).sum(-1)
+    assert sq.shape == (B, S) and torch.allclose(sq, want, rtol=1e-5, atol=1e-6)
+    Va = V.detach().clone().requires_grad_()
+    Vb = V.detach().clone().requires_grad_()
+    Tb = T.detach().clone().requires_grad_()
+    up = O.rn(603, B, 40).cuda() / 40
+    s0 = Fk.pacl_scores(Va, T, 10.0, "sigmoid")
+    s0.backward(up)
+    s1 = Fk.pacl_scores(Vb, Tb, 10.0, "sigmoid", None, sq)
+    s1.backward(up)
+    assert (s0 - s1).abs().max().item() < 1e-3
+    assert rel_l2(Vb.grad.float(), Va.grad.float()) < 1e-3 and rel_l2(Tb.grad.float(), T.grad.float()) < 1e-3
