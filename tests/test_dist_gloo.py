@@ -63,7 +63,7 @@ def _patch_cpu_kernels():
     Fk._k_ce_rows, Fk._k_ce_cols, Fk._k_ce_scores_grad = k_rows, k_cols, k_grad
     Fk._k_ce_payload, Fk._k_ce_merge = k_payload, k_merge
     Fk._need_cuda = lambda *a: None
-    Fk.pacl_scores = lambda V, T, c=1.0, activation="sigmoid", group=None: O.pacl_allpairs_scores(V, T, c, activation)
+    Fk.pacl_scores = lambda V, T, c=1.0, activation="sigmoid", group=None, v_sqnorm=None: O.pacl_allpairs_scores(V, T, c, activation)
     # SPARC host logic: CPU stand-ins for the row kernels and the local term
     Fk.normalize_rows = O.l2n
     Fk.mean_dim1 = lambda X: X.float().mean(dim=1)
