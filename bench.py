@@ -346,30 +346,33 @@ def run_gpu(args):
     launches = (_lib.lib().clipk_launch_count() - lc0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- engine-only time (roofline): events around the scoring forward and backward of each step -------------
+    # ---- engine-only time (roofline): the scoring forward + backward alone (no InfoNCE, no collectives), `steps` iterations
+    # back to back between two CUDA events, after one untimed iteration of this call pattern
     import clip_embeds_b200.functional as Fk
-    eng_samples = []
-    for _ in range(min(args.steps, 5) + 1):
-        Vt = V.detach().requires_grad_()
-        Tt = T.detach()
-        if world > 1:
-            Tall = torch.empty(B_GLOBAL, D, dtype=T.dtype, device=dev)
-            dist.all_gather_into_tensor(Tall, Tt)
-        else:
-            Tall = Tt
-        Tall = Tall.requires_grad_()
-        g = torch.randn(b, B_GLOBAL, device=dev) / B_GLOBAL
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        torch.cuda.synchronize()
-        e[0].record()
-        s = Fk.pacl_scores(Vt, Tall, 1.0 / TEMPERATURE)
-        e[1].record()
-        e[2].record()
-        s.backward(g)
-        e[3].record()
-        torch.cuda.synchronize()
-        eng_samples.append(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]))
-    eng_ms = statistics.median(eng_samples[1:])        # first pass is an untimed warm-up of this call pattern
+    Vt = V.detach().requires_grad_()
+    Tt = T.detach()
+    if world > 1:
+        Tall = torch.empty(B_GLOBAL, D, dtype=T.dtype, device=dev)
+        dist.all_gather_into_tensor(Tall, Tt)
+    else:
+        Tall = Tt
+    Tall = Tall.requires_grad_()
+    g = torch.randn(b, B_GLOBAL, device=dev) / B_GLOBAL
+
+    def engine_step():
+        Vt.grad = None
+        Tall.grad = None
+        Fk.pacl_scores(Vt, Tall, 1.0 / TEMPERATURE).backward(g)
+
+    engine_step()
+    torch.cuda.synchronize()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for _ in range(args.steps):
+        engine_step()
+    ee1.record()
+    torch.cuda.synchronize()
+    eng_ms = ee0.elapsed_time(ee1) / args.steps
 
     # ---- timed region 2: end to end from pinned host buffers (e2e) ---------------------------------------------
     copy_stream = torch.cuda.Stream()
