@@ -48,7 +48,7 @@ SIGNATURES = {
     "clipk_ce_sym_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_vp,
                                  c_vp, c_vp, c_vp, c_sz, c_vp]),
     "clipk_ce_sym_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_vp,
-                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_sz, c_vp]),
     "clipk_ce_feat_bwd_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_sz, c_vp]),
     "clipk_sparc_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),

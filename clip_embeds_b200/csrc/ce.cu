@@ -778,6 +778,7 @@ struct CeSymBwd {           // column part of the symmetric backward (null col_b
   const float* col_bias = nullptr;
   const float* col_w = nullptr;
   int ncol = 0;
+  int phase = 0;            // 0: dL, dX, dY;  1: dL + dY only;  2: dX only from the dL phase 1 left in the workspace
 };
 
 int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, int D, float scale, float bias,
@@ -805,7 +806,9 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       OperandDesc a, b;
       a.ptr = X + (int64_t)m0 * D; a.rows = mc; a.k = D; a.ld = D;
       b.ptr = Y; b.rows = N; b.k = D; b.ld = D;
-      if (sym.col_bias != nullptr) {
+      if (sym.phase == 2) {
+        // dL of this (single) row chunk is still in the workspace
+      } else if (sym.col_bias != nullptr) {
         epi::DlSymTma::Params ep{{w.dL, ldd, (int64_t)mc * ldd, mc, N, 1}, row_lse + m0, row_w + m0, label_offset + m0, mc, N,
                                  scale, bias, scale_dev, slab_counts, slab_n0, slab_rows, sym.col_bias, sym.col_w, sym.ncol};
         CLIPK_TRY((launch_gemm2<256, false, false, epi::DlSymTma>(&a, &b, 1, ksD, ksD, mc, N, 1, ep, st)));
@@ -821,7 +824,9 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
     }
     // dX[m0:m0+mc] (+)= scale * dL Y          (A = dL K-major over n, B = Y MN-major)
     const DxSplit sp = dx_split(mc, N, D);
-    if (dX != nullptr && sp.nsplit > 1 && w.slabs != nullptr && D % 4 == 0) {
+    if (sym.phase == 1) {
+      // the caller wants dY first (its reduce-scatter overlaps the dX GEMM of phase 2)
+    } else if (dX != nullptr && sp.nsplit > 1 && w.slabs != nullptr && D % 4 == 0) {
       // split-K: the splits are the batches of ONE launch (slab s = batch s); batch s starts at column s * ksplit of
       // the single long reduction dim, the operand maps keep the true extent N, so the last split's tail is
       // zero-filled by TMA; then a fixed-order slab sum
@@ -857,7 +862,7 @@ int ce_feat_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, int M, int N, in
       }
     }
     // dY (+)= scale * dL^T X[m0:m0+mc]        (A = dL MN-major (rows = n), B = X MN-major)
-    if (dY != nullptr) {
+    if (dY != nullptr && sym.phase != 2) {
       OperandDesc a, b;
       a.ptr = w.dL; a.mn_major = true; a.rows = N; a.k = mc; a.ld = ldd;
       b.ptr = X + (int64_t)m0 * D; b.mn_major = true; b.rows = D; b.k = mc; b.ld = D;
@@ -1004,13 +1009,16 @@ int clipk_ce_sym_fwd(const void* X, const void* Y, int M, int N, int D, float sc
 int clipk_ce_sym_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
                      const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol,
                      const float* row_lse, const float* row_w, const float* col_bias, const float* col_w, void* dX,
-                     void* dY, int grads_bf16, void* workspace, size_t ws_bytes, void* stream) {
+                     void* dY, int grads_bf16, int phase, void* workspace, size_t ws_bytes, void* stream) {
   CLIPK_TRY(clipk::check_device());
   CLIPK_REQUIRE(col_bias != nullptr && col_w != nullptr && ncol > 0 && ncol <= N, "ce_sym_bwd: column terms missing");
+  CLIPK_REQUIRE(phase >= 0 && phase <= 2 && (phase == 0 || M <= clipk::kCeChunkRows),
+                "ce_sym_bwd: the two-phase backward needs a single row chunk (M=%d <= %d)", M, clipk::kCeChunkRows);
   clipk::CeSymBwd sym;
   sym.col_bias = col_bias;
   sym.col_w = col_w;
   sym.ncol = ncol;
+  sym.phase = phase;
   return clipk::ce_feat_bwd(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(Y), M, N, D, scale,
                             bias, scale_dev, slab_counts, slab_n0, slab_rows, nullptr, label_offset, row_lse, row_w, dX, 0,
                             dY, 0, grads_bf16, workspace, ws_bytes, static_cast<cudaStream_t>(stream), sym);

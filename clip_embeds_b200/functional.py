@@ -603,12 +603,125 @@ class _SymFeatCE(torch.autograd.Function):
         ws = ctx.ws
         _lib.call("clipk_ce_sym_bwd", Xc.data_ptr(), Yc.data_ptr(), M, N, D, sc, bi, scale_dev.data_ptr() if dev_scale else 0,
                   sl_ptr, slab_n0, slab_rows, off, n0, row_lse.data_ptr(), row_w.data_ptr(), col_bias.data_ptr(),
-                  col_w.data_ptr(), dX.data_ptr(), dY.data_ptr(), 1 if bf16_out else 0, ws.data_ptr(), ws.numel(), _stream())
+                  col_w.data_ptr(), dX.data_ptr(), dY.data_ptr(), 1 if bf16_out else 0, 0, ws.data_ptr(), ws.numel(), _stream())
         dscale = None
         if scale_grad:                 # d/dscale of sum(dlogits * x.y) = <dX, X> / scale
             dscale = ((dX.float() * Xc.float()).sum() / (scale_dev.reshape(()) if dev_scale else sc)).reshape(scale_shape)
         dbias = torch.zeros((), device=dev) if bias_tensor else None
         return dX.to(xdt), dY.to(ydt), dscale, dbias, None, None, None, None
+
+
+class _SymFeatCEDist(torch.autograd.Function):
+    """_SymFeatCE with the caption exchange inside (open_clip local loss, `gather_with_grad`, optional `usehardtext`):
+    forward all-gathers this rank's captions (fixed-capacity slabs + device-side fill counts when there are hard
+    negatives), backward reduce-scatters the caption gradient ITSELF -- started right after the dY GEMM so that it runs
+    over NVLink while the dX GEMM is still on the tensor cores (two-phase clipk_ce_sym_bwd)."""
+
+    @staticmethod
+    def forward(ctx, X, txt, scale, bias, rank, world, b, usehardtext, group):
+        import torch.distributed as dist
+        _need_cuda(X, txt)
+        dev = X.device
+        D = X.shape[1]
+        Xc, tc = X.contiguous(), txt.contiguous()
+        h = tc.shape[0] - b
+        rows = 2 * b if usehardtext else b                  # rows every rank contributes to the gather
+        if tc.shape[0] < rows:
+            tc_pad = torch.cat([tc, tc.new_zeros((rows - tc.shape[0], D))], dim=0)
+        else:
+            tc_pad = tc
+        gathered = torch.empty(world * rows, D, dtype=tc.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, tc_pad, group=group)
+        n0 = world * b
+        if usehardtext:
+            counts = torch.empty(world, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(counts, torch.tensor([h], dtype=torch.int32, device=dev), group=group)
+            g3 = gathered.reshape(world, rows, D)
+            Y = torch.cat([g3[:, :b].reshape(n0, D), g3[:, b:].reshape(n0, D)], dim=0)       # [originals | slabs]
+            slab_counts, slab_n0, slab_rows = counts, n0, b
+        else:
+            Y = gathered
+            slab_counts, slab_n0, slab_rows = None, 0, 0
+        M, N = Xc.shape[0], Y.shape[0]
+        off = b * rank
+        scale_dev = None
+        if torch.is_tensor(scale) and scale.is_cuda:
+            scale_dev = scale.detach().to(torch.float32).reshape(1).contiguous()
+            sc = 1.0
+        else:
+            sc = float(scale)
+        bi = float(bias) if bias is not None else 0.0
+        st = _stream()
+        row_lse, row_loss, col_sum = _f32(M, device=dev), _f32(M, device=dev), _f32(n0, device=dev)
+        nbytes = _lib.lib().clipk_ce_feat_bwd_workspace_bytes(M, N, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("clipk_ce_sym_fwd", Xc.data_ptr(), Y.data_ptr(), M, N, D, sc, bi, _p(scale_dev), _p(slab_counts), slab_n0,
+                  slab_rows, off, n0, row_lse.data_ptr(), row_loss.data_ptr(), col_sum.data_ptr(), ws.data_ptr(), nbytes, st)
+        dist.all_reduce(col_sum, op=dist.ReduceOp.SUM, group=group)
+        s_t = scale_dev.reshape(()) if scale_dev is not None else torch.tensor(sc, device=dev)
+        col_lse = 0.5 * s_t + bi + torch.log(col_sum)
+        pos = row_lse - row_loss
+        loss = 0.5 * (row_loss.mean() + (col_lse[off:off + M] - pos).mean())
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(Xc, Y, row_lse, col_lse, scale_dev if scale_dev is not None else empty,
+                              slab_counts if slab_counts is not None else empty)
+        ctx.cfg = (sc, bi, off, n0, (slab_n0, slab_rows) if slab_counts is not None else None, scale_dev is not None,
+                   torch.is_tensor(scale) and scale.requires_grad, scale.shape if torch.is_tensor(scale) else None, X.dtype,
+                   txt.dtype, torch.is_tensor(bias), world, b, rows, tc.shape[0], bool(usehardtext))
+        ctx.ws = ws
+        ctx.group = group
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        Xc, Y, row_lse, col_lse, scale_dev, slab_counts = ctx.saved_tensors
+        (sc, bi, off, n0, slab_geo, dev_scale, scale_grad, scale_shape, xdt, tdt, bias_tensor, world, b, rows, ntxt,
+         hard) = ctx.cfg
+        M, D = Xc.shape
+        N = Y.shape[0]
+        dev = Xc.device
+        w = (g.float() * (0.5 / M)).reshape(1)
+        row_w = w.expand(M).contiguous()
+        col_w = w.expand(n0).contiguous()
+        col_bias = (torch.log(col_w) - col_lse).contiguous()
+        sl_ptr = slab_counts.data_ptr() if slab_geo is not None else 0
+        slab_n0, slab_rows = slab_geo if slab_geo is not None else (0, 0)
+        two_phase = M <= 4096 and M > 128 and N > 128
+        bf16_out = two_phase and not scale_grad
+        gdt = torch.bfloat16 if bf16_out else torch.float32
+        dX = torch.empty(M, D, dtype=gdt, device=dev)
+        dY = torch.empty(N, D, dtype=gdt, device=dev)
+        ws = ctx.ws
+
+        def run(phase):
+            _lib.call("clipk_ce_sym_bwd", Xc.data_ptr(), Y.data_ptr(), M, N, D, sc, bi, scale_dev.data_ptr() if dev_scale else 0,
+                      sl_ptr, slab_n0, slab_rows, off, n0, row_lse.data_ptr(), row_w.data_ptr(), col_bias.data_ptr(),
+                      col_w.data_ptr(), dX.data_ptr(), dY.data_ptr(), 1 if bf16_out else 0, phase, ws.data_ptr(), ws.numel(),
+                      _stream())
+
+        run(1 if two_phase else 0)
+        # caption gradient back to its owners: [originals | slabs] -> [W][rows][D], reduce-scatter(SUM)
+        if hard:
+            send = torch.cat([dY[:n0].reshape(world, b, D), dY[n0:].reshape(world, b, D)], dim=1).contiguous()
+        else:
+            send = dY.reshape(world, rows, D)
+        d_txt_pad = torch.empty(rows, D, dtype=gdt, device=dev)
+        work = dist.reduce_scatter_tensor(d_txt_pad, send.reshape(world * rows, D), op=dist.ReduceOp.SUM, group=ctx.group,
+                                          async_op=True)
+        if two_phase:
+            run(2)                     # the dX GEMM runs while the reduce-scatter is on the wire
+        work.wait()
+        dscale = None
+        if scale_grad:
+            dscale = ((dX.float() * Xc.float()).sum() / (scale_dev.reshape(()) if dev_scale else sc)).reshape(scale_shape)
+        dbias = torch.zeros((), device=dev) if bias_tensor else None
+        return dX.to(xdt), d_txt_pad[:ntxt].to(tdt), dscale, dbias, None, None, None, None, None
+
+
+def sym_feat_ce_dist(X, text_local, scale, bias, rank, world, b, usehardtext, group):
+    """See _SymFeatCEDist: this rank's local-loss share with the caption gather / gradient reduce-scatter inside."""
+    return _SymFeatCEDist.apply(X, text_local, scale, bias, int(rank), int(world), int(b), bool(usehardtext), group)
 
 
 def sym_feat_ce(X, Y_all, scale, bias=0.0, offset=0, n_orig=None, slab=None, group=None):

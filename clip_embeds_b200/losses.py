@@ -117,17 +117,9 @@ class OpenClipLoss(nn.Module):
                 not self.usehardtext or b % 32 == 0):
             # local loss, one GEMM per rank: local image rows x all captions; the column sums are all-reduced, the image
             # features are never gathered, the caption gradient goes back through the gather's reduce-scatter
-            pg = self.group
-            off = b * self.rank
-            if self.usehardtext:
-                _, all_txt, counts = cdist.gather_features(None, text_features, b, True, True, True, self.rank,
-                                                           self.world_size, pg, keep_padding=True)
-                slab = (counts, self.world_size * b, b)
-            else:
-                all_txt = cdist.all_gather_with_grad(text_features, pg)
-                slab = None
-            total = Fk.sym_feat_ce(image_features, all_txt, logit_scale, bias, off, self.world_size * b, slab,
-                                   pg if pg is not None else torch.distributed.group.WORLD)
+            pg = self.group if self.group is not None else torch.distributed.group.WORLD
+            total = Fk.sym_feat_ce_dist(image_features, text_features, logit_scale, bias, self.rank, self.world_size, b,
+                                        self.usehardtext, pg)
             return {"contrastive_loss": total} if output_dict else total
         if self.world_size > 1:
             if self.usehardtext:

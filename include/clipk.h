@@ -173,14 +173,16 @@ int clipk_ce_feat_bwd(const void* X, const void* Y, int M, int N, int D, float s
  * Backward: dL = row_w[m] (softmax_row - onehot) + (exp(logit + col_bias[j]) - col_w[lab] onehot), with
  *   col_bias[j] = log(col_w[j]) - col_lse[j]; dX [M,D] and dY [N,D] (this rank's partial: sum it over the ranks) in fp32
  *   (grads_bf16 = 0) or bf16 (grads_bf16 = 1, M <= 4096).  bf16 features, CTA-pair tcgen05 engine, logits never written;
- *   workspace as clipk_ce_feat_bwd_workspace_bytes(M, N, D).  scale_dev / slab_* as above. */
+ *   workspace as clipk_ce_feat_bwd_workspace_bytes(M, N, D).  scale_dev / slab_* as above.
+ *   phase (M <= 4096): 0 = everything; 1 = dL + dY only, 2 = dX only from the dL that phase 1 left in the workspace -- the
+ *   caller starts the reduce-scatter of dY between the two calls so that it overlaps the dX GEMM. */
 int clipk_ce_sym_fwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
                      const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol, float* row_lse,
                      float* row_loss, float* col_sum, void* workspace, size_t ws_bytes, void* stream);
 int clipk_ce_sym_bwd(const void* X, const void* Y, int M, int N, int D, float scale, float bias, const float* scale_dev,
                      const int* slab_counts, int slab_n0, int slab_rows, int64_t label_offset, int ncol,
                      const float* row_lse, const float* row_w, const float* col_bias, const float* col_w, void* dX,
-                     void* dY, int grads_bf16, void* workspace, size_t ws_bytes, void* stream);
+                     void* dY, int grads_bf16, int phase, void* workspace, size_t ws_bytes, void* stream);
 
 /* The same backward with bf16 gradients written straight from the GEMM epilogues (dX, dY bf16, both required, no
  * accumulation); supported for 128 < M <= 4096 and N > 128 (CLIPK_ERR_INVALID otherwise: use the fp32 entry). */
