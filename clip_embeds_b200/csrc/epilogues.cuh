@@ -380,6 +380,9 @@ struct DsDual {
   __device__ void chunk2(int b, int, int n, float* x, float* d, const Side& rn_l) {
     const int lane = (int)ptx::lane_id();
     const int col = n + lane;
+#ifdef CLIPK_EPI_STUB
+    if (p.act == 77) return;      // timing experiment: no epilogue math (garbage results)
+#endif
     if (p.act == CLIPK_ACT_ONES) {                       // warp-uniform: a = 1, ds = 0
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -673,7 +673,7 @@ static int allpairs_bwd_pooled(const __nv_bfloat16* V, const __nv_bfloat16* T, i
       const int ks[1] = {(D + 63) / 64};
       const eng::OutDesc oe{w.E, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // extent P: pad columns clipped on store,
       const eng::OutDesc oa{w.A, Ppad, (int64_t)Bt * Ppad, Bt, P, gi};      // zero-filled on load
-      epi::DsDual::Params ep{oe, oa, rnV0, alpha0, beta0, dsdot0, Bt, P, act};
+      epi::DsDual::Params ep{oe, oa, rnV0, alpha0, beta0, dsdot0, Bt, P, env_int("CLIPK_DBG_ACT", act)};
       if (Ppad >= 128) CLIPK_TRY((launch_gemm2<128, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
       else CLIPK_TRY((launch_gemm2<64, false, false, epi::DsDual>(a, &b, 1, ks, ks, Bt, Ppad, gi, ep, ls)));
     }
